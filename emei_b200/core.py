@@ -1,0 +1,201 @@
+"""Batched, device-resident counterpart of the reference's API contract ``emei/core.py``.
+
+Mirrors ``Freezable`` (core.py:18-37) and ``EmeiEnv`` (core.py:131-193): same method names,
+argument meaning and error behaviour, with arrays generalised to ``[num_envs, dim]`` CUDA tensors.
+numpy inputs are accepted everywhere (copied to the device; results come back as numpy), so code
+written against the reference's ``get_batch_*`` keeps working unchanged.
+
+Out of scope: the offline-dataset download/h5 loader of
+``OfflineEnv`` (core.py:40-128) -- ``dataset_names`` is empty and ``get_dataset`` raises.
+"""
+from typing import Dict, Union
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+class Freezable:
+    """core.py:18-37."""
+
+    def __init__(self):
+        self.frozen_state = None
+        self.frozen = False
+
+    def freeze(self):
+        assert not self.frozen, "env has frozen"
+        self.frozen = True
+
+    def unfreeze(self):
+        assert self.frozen, "env has unfrozen"
+        self.frozen = False
+
+
+def _torch_dtype(dtype) -> torch.dtype:
+    if isinstance(dtype, torch.dtype):
+        out = dtype
+    else:
+        out = {"float32": torch.float32, "float64": torch.float64}[np.dtype(dtype).name]
+    if out not in (torch.float32, torch.float64):
+        raise ValueError("emei_b200 computes in float32 or float64")
+    return out
+
+
+class EmeiEnv(Freezable):
+    """core.py:131-193, batched.  ``num_envs`` environments live in one set of device buffers."""
+
+    def __init__(
+        self,
+        env_params: Dict[str, Union[str, int, float]],
+        num_envs: int = 1,
+        device: Union[str, torch.device, None] = None,
+        dtype=torch.float32,
+    ):
+        Freezable.__init__(self)
+        self.env_name = self.__class__.__name__[:-3]  # core.py:42
+        self.env_params = env_params
+        self.num_envs = int(num_envs)
+        if self.num_envs < 1:
+            raise ValueError("num_envs must be >= 1")
+        self._device_arg = device
+        self._device = None
+        self.dtype = _torch_dtype(dtype)
+        self._suffix = "_f32" if self.dtype == torch.float32 else "_f64"
+        self._transition_graph = None
+        self._reward_mech_graph = None
+        self._termination_mech_graph = None
+        self._stats = None
+        self._seed = 0
+        self._reset_count = 0
+
+    # ------------------------------------------------------------------ device plumbing
+    @property
+    def device(self) -> torch.device:
+        if self._device is None:
+            if not torch.cuda.is_available():
+                raise _lib.EmeiB200Error("emei_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+            d = torch.device("cuda", torch.cuda.current_device()) if self._device_arg is None else torch.device(self._device_arg)
+            if d.type != "cuda":
+                raise _lib.EmeiB200Error(f"emei_b200 runs on CUDA devices only, got {d}")
+            if d.index is None:
+                d = torch.device("cuda", torch.cuda.current_device())
+            self._device = d
+        return self._device
+
+    def _stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def _to_device(self, x, dtype=None, non_blocking=True):
+        """-> (contiguous device tensor, came_from_host_numpy)."""
+        if x is None:
+            return None, False
+        was_np = not isinstance(x, torch.Tensor)
+        t = torch.as_tensor(x) if was_np else x
+        if dtype is not None and t.dtype != dtype:
+            t = t.to(dtype)
+        if t.device != self.device:
+            t = t.to(self.device, non_blocking=non_blocking)
+        return t.contiguous(), was_np
+
+    @staticmethod
+    def _ret(t: torch.Tensor, as_numpy: bool):
+        return t.cpu().numpy() if as_numpy else t
+
+    def _call(self, base: str, *args, launches=1):
+        with torch.cuda.device(self.device):
+            _lib.call(base + self._suffix, *args, launches=launches)
+
+    # ------------------------------------------------------------------ statistics (rollout returns)
+    @property
+    def stats(self) -> torch.Tensor:
+        """device double[2] = [sum of rewards, number of done flags] accumulated by every kernel call."""
+        if self._stats is None:
+            self._stats = torch.zeros(2, dtype=torch.float64, device=self.device)
+        return self._stats
+
+    def reset_stats(self):
+        with torch.cuda.device(self.device):
+            _lib.call("emei_stats_reset", self.stats.data_ptr(), self._stream(), launches=0)
+
+    def read_stats(self, group=None):
+        """(return_sum, done_count) over ALL ranks of ``group`` when torch.distributed is initialised
+        (one NCCL all-reduce of 2 doubles), else over this process."""
+        from .dist import all_reduce_sum_
+
+        s = all_reduce_sum_(self.stats.clone(), group)
+        r, d = s.tolist()
+        return r, int(round(d))
+
+    # ------------------------------------------------------------------ core.py contract
+    @property
+    def dataset_names(self) -> list:
+        return []
+
+    def get_dataset(self, dataset_name: str):
+        raise NotImplementedError("offline h5 datasets (core.py:40-128) are outside the emei_b200 hot path")
+
+    @property
+    def env_params_name(self):
+        # core.py:56-58
+        return "&".join("{}={}".format(key, self.env_params[key]) for key in sorted(self.env_params.keys()))
+
+    def get_transition_graph(self, repeat_times=1):
+        """core.py:142-161.  Envs without a graph raise AttributeError in the reference
+        (``None.copy()``); here the error says why."""
+        if self._transition_graph is None:
+            raise AttributeError(f"{type(self).__name__} defines no transition graph (the reference has none for it)")
+        g = self._transition_graph.copy()
+        num_obs, num_action = self.observation_space.shape[0], self.action_space.shape[0]
+        assert g.shape == (num_obs + num_action, num_obs)
+        if repeat_times == 1:
+            return g
+        n = num_obs + num_action
+        aug_g = np.zeros([n, n])
+        aug_g[:, :num_obs] = g
+        prod_g, sum_g = aug_g.copy(), np.zeros([n, n])
+        for _ in range(repeat_times):
+            sum_g += prod_g
+            prod_g = np.matmul(prod_g, aug_g)
+        return (sum_g > 0).astype(int)[:, :num_obs]
+
+    def get_reward_mech_graph(self):
+        return self._reward_mech_graph
+
+    def get_termination_mech_graph(self):
+        return self._termination_mech_graph
+
+    def transform_state_to_obs(self, batch_state):
+        return batch_state.clone() if isinstance(batch_state, torch.Tensor) else np.array(batch_state, copy=True)
+
+    def transform_obs_to_state(self, batch_obs):
+        return batch_obs.clone() if isinstance(batch_obs, torch.Tensor) else np.array(batch_obs, copy=True)
+
+    def get_batch_init_state(self, batch_size):
+        raise NotImplementedError
+
+    def get_batch_init_obs(self, batch_size):
+        return self.transform_state_to_obs(self.get_batch_init_state(batch_size=batch_size))
+
+    def get_batch_reward(self, obs, pre_obs=None, action=None, state=None, pre_state=None):
+        raise NotImplementedError
+
+    def get_batch_terminal(self, obs, pre_obs=None, action=None, state=None, pre_state=None):
+        raise NotImplementedError
+
+    def get_batch_next_obs(self, obs, pre_obs=None, action=None, state=None, pre_state=None):
+        assert self.frozen
+        raise NotImplementedError
+
+    # ------------------------------------------------------------------ seeding (gym.Env.reset(seed=))
+    def _reseed(self, seed):
+        if seed is not None:
+            self._seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+            self._reset_count = 0
+
+    def _next_sample_seed(self):
+        """A fresh Philox key per sampling call: (seed, call counter) so repeated resets differ but a
+        given (seed, call index) is reproducible and independent of sharding."""
+        s = (self._seed * 0x9E3779B97F4A7C15 + self._reset_count * 0xD1B54A32D192ED03) & 0xFFFFFFFFFFFFFFFF
+        self._reset_count += 1
+        return s

@@ -1,0 +1,261 @@
+"""Device-buffer owners behind the env classes: they hold the state tensors, build the POD
+parameter structs and issue the C-ABI calls.  No arithmetic happens in Python.
+
+HBM layout:
+  cart-pole / IP : state  [B,4] row-major (one 128-bit row per env), ping-pong pair of buffers;
+                   IP keeps a separate obs buffer (theta wrapped) because the reference wraps only
+                   the observation copy (inverted_pendulum.py:45-49).
+  charged ball   : on_circle uint8[B], circle [B,2], free [B,4] (= observation), updated in place.
+  outputs        : reward [B,1] (engine dtype), done uint8[B,1] viewed as torch.bool.
+"""
+import ctypes
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+
+_ACTION_KIND = {
+    torch.uint8: _lib.ACTION_DISCRETE_U8,
+    torch.bool: _lib.ACTION_DISCRETE_U8,
+    torch.int32: _lib.ACTION_DISCRETE_I32,
+    torch.int64: _lib.ACTION_DISCRETE_I64,
+    torch.float32: _lib.ACTION_CONTINUOUS_F32,
+    torch.float64: _lib.ACTION_CONTINUOUS_F64,
+}
+
+
+def normalise_action(env, action, continuous: bool) -> torch.Tensor:
+    """-> contiguous device tensor [num_envs] in one of the encodings of include/emei_b200.h.
+    Mirrors base_control.py:62-66 (int -> array; action_space.contains) for a batch."""
+    n = env.num_envs
+    if isinstance(action, (int, np.integer)) and not continuous:
+        action = torch.full((n,), int(action), dtype=torch.int64)
+    a, _ = env._to_device(action)
+    if a.numel() != n:
+        raise AssertionError(f"{action!r} ({type(action)}) invalid: expected {n} actions, got shape {tuple(a.shape)}")
+    a = a.reshape(n)
+    if continuous:
+        if a.dtype not in (torch.float32, torch.float64):
+            a = a.to(torch.float32)
+    else:
+        if a.dtype.is_floating_point:
+            raise AssertionError(f"{action!r} ({type(action)}) invalid: discrete action space needs integers")
+        if a.dtype not in _ACTION_KIND:
+            a = a.to(torch.int64)
+    if env.validate_actions:  # device-side range check: one sync, off by default
+        if continuous:
+            lo, hi = float(env.action_space.low.min()), float(env.action_space.high.max())
+            ok = bool(((a >= lo) & (a <= hi)).all())
+        else:
+            ok = bool(((a >= 0) & (a < env.action_space.n)).all())
+        assert ok, f"{action!r} ({type(action)}) invalid"
+    return a.contiguous()
+
+
+class StepOutputs:
+    """Ping-pong output buffers: what step t returns stays valid until step t+2 overwrites it."""
+
+    def __init__(self, n, dtype, device):
+        self.reward = [torch.empty((n, 1), dtype=dtype, device=device) for _ in range(2)]
+        self.done = [torch.empty((n, 1), dtype=torch.uint8, device=device) for _ in range(2)]
+
+
+class CartPoleEngine:
+    """cart-pole family + analytic inverted pendulum (emei_cartpole_step_*)."""
+
+    def __init__(self, env, params: _lib.CartPoleParams, separate_obs: bool):
+        self.env = env
+        self.params = params
+        self.separate_obs = separate_obs
+        self.n = env.num_envs
+        self._bufs = None
+        self._obs = None
+        self._out = None
+        self._cur = 0
+        self.has_state = False
+
+    def _alloc(self):
+        if self._bufs is None:
+            dev, dt = self.env.device, self.env.dtype
+            self._bufs = [torch.empty((self.n, 4), dtype=dt, device=dev) for _ in range(2)]
+            if self.separate_obs:
+                self._obs = [torch.empty((self.n, 4), dtype=dt, device=dev) for _ in range(2)]
+            self._out = StepOutputs(self.n, dt, dev)
+
+    @property
+    def state(self) -> Optional[torch.Tensor]:
+        return self._bufs[self._cur] if self.has_state else None
+
+    def set_state(self, state):
+        self._alloc()
+        s, _ = self.env._to_device(state, self.env.dtype)
+        if tuple(s.shape) != (self.n, 4):
+            raise ValueError(f"state must have shape {(self.n, 4)}, got {tuple(s.shape)}")
+        self._bufs[self._cur].copy_(s)
+        self.has_state = True
+
+    def step(self, action: torch.Tensor, copy_obs: bool):
+        env = self.env
+        self._alloc()
+        src, dst = self._bufs[self._cur], self._bufs[1 - self._cur]
+        nxt = 1 - self._cur
+        obs = None
+        if self.separate_obs:
+            obs = self._obs[nxt] if not copy_obs else torch.empty_like(src)
+        elif copy_obs:
+            obs = torch.empty_like(src)
+        reward, done = self._out.reward[nxt], self._out.done[nxt]
+        if copy_obs:
+            reward, done = torch.empty_like(reward), torch.empty_like(done)
+        self.params.action_kind = _ACTION_KIND[action.dtype]
+        env._call(
+            "emei_cartpole_step",
+            src.data_ptr(), dst.data_ptr(), obs.data_ptr() if obs is not None else None, action.data_ptr(),
+            reward.data_ptr(), done.data_ptr(), env.stats.data_ptr(), self.n, ctypes.byref(self.params), env._stream(),
+        )
+        self._cur = nxt
+        return (obs if obs is not None else dst), reward, done.view(torch.bool)
+
+    def next_obs_stateless(self, obs: torch.Tensor, action: torch.Tensor):
+        """get_batch_next_obs: one dynamics step from caller-supplied observations (any batch size);
+        the engine's own state is untouched."""
+        env = self.env
+        b = obs.shape[0]
+        out = torch.empty_like(obs)
+        obs_out = torch.empty_like(obs) if self.separate_obs else None
+        reward = torch.empty((b, 1), dtype=env.dtype, device=env.device)
+        done = torch.empty((b, 1), dtype=torch.uint8, device=env.device)
+        self.params.action_kind = _ACTION_KIND[action.dtype]
+        env._call(
+            "emei_cartpole_step",
+            obs.data_ptr(), out.data_ptr(), obs_out.data_ptr() if obs_out is not None else None, action.data_ptr(),
+            reward.data_ptr(), done.data_ptr(), None, b, ctypes.byref(self.params), env._stream(),
+        )
+        return obs_out if obs_out is not None else out
+
+    # freeze/unfreeze: device-side snapshot of the live state buffer (base_control.py:32-36)
+    def snapshot(self):
+        src = self._bufs[self._cur]
+        snap = torch.empty_like(src)
+        with torch.cuda.device(self.env.device):
+            _lib.call("emei_snapshot_copy", snap.data_ptr(), src.data_ptr(), src.numel() * src.element_size(), self.env._stream())
+        return snap
+
+    def restore(self, snap: torch.Tensor):
+        self._alloc()
+        dst = self._bufs[self._cur]
+        with torch.cuda.device(self.env.device):
+            _lib.call("emei_snapshot_copy", dst.data_ptr(), snap.data_ptr(), snap.numel() * snap.element_size(), self.env._stream())
+        self.has_state = True
+
+
+class ChargedBallEngine:
+    """charged ball (emei_charged_ball_step_*): three state arrays updated in place."""
+
+    def __init__(self, env, params: _lib.ChargedBallParams):
+        self.env = env
+        self.params = params
+        self.n = env.num_envs
+        self.on_circle = self.circle = self.free = None
+        self._out = None
+        self._flip = 0
+        self.has_state = False
+
+    def _alloc(self):
+        if self.on_circle is None:
+            dev, dt = self.env.device, self.env.dtype
+            self.on_circle = torch.empty((self.n,), dtype=torch.uint8, device=dev)
+            self.circle = torch.empty((self.n, 2), dtype=dt, device=dev)
+            self.free = torch.empty((self.n, 4), dtype=dt, device=dev)
+            self._out = StepOutputs(self.n, dt, dev)
+
+    def set_state(self, on_circle, circle, free):
+        self._alloc()
+        env = self.env
+        self.on_circle.copy_(env._to_device(on_circle, torch.uint8)[0].reshape(self.n))
+        self.circle.copy_(env._to_device(circle, env.dtype)[0].reshape(self.n, 2))
+        self.free.copy_(env._to_device(free, env.dtype)[0].reshape(self.n, 4))
+        self.has_state = True
+
+    def sample_initial(self, seed: int, env_offset: int):
+        self._alloc()
+        self.env._call(
+            "emei_init_charged_ball", self.on_circle.data_ptr(), self.circle.data_ptr(), self.free.data_ptr(), self.n,
+            float(self.params.radius), ctypes.c_uint64(seed), ctypes.c_uint64(env_offset), self.env._stream(),
+        )
+        self.has_state = True
+
+    def step(self, action: torch.Tensor, copy_obs: bool):
+        env = self.env
+        self._flip ^= 1
+        reward, done = self._out.reward[self._flip], self._out.done[self._flip]
+        if copy_obs:
+            reward, done = torch.empty_like(reward), torch.empty_like(done)
+        self.params.action_kind = _ACTION_KIND[action.dtype]
+        env._call(
+            "emei_charged_ball_step",
+            self.on_circle.data_ptr(), self.circle.data_ptr(), self.free.data_ptr(), action.data_ptr(),
+            reward.data_ptr(), done.data_ptr(), env.stats.data_ptr(), self.n, ctypes.byref(self.params), env._stream(),
+        )
+        obs = self.free.clone() if copy_obs else self.free
+        return obs, reward, done.view(torch.bool)
+
+    def snapshot(self):
+        out = []
+        with torch.cuda.device(self.env.device):
+            for src in (self.on_circle, self.circle, self.free):
+                snap = torch.empty_like(src)
+                _lib.call("emei_snapshot_copy", snap.data_ptr(), src.data_ptr(), src.numel() * src.element_size(), self.env._stream())
+                out.append(snap)
+        return tuple(out)
+
+    def restore(self, snaps):
+        self._alloc()
+        with torch.cuda.device(self.env.device):
+            for dst, snap in zip((self.on_circle, self.circle, self.free), snaps):
+                _lib.call("emei_snapshot_copy", dst.data_ptr(), snap.data_ptr(), snap.numel() * snap.element_size(), self.env._stream())
+        self.has_state = True
+
+
+def score(env, params: _lib.ScoringParams, obs, pre_obs=None, action=None, want="both", group=None):
+    """Fused get_batch_reward + get_batch_terminal through emei_reward_terminal_* for any batch size.
+
+    Hopper/HalfCheetah: pass 1 = emei_sumsq_* over the action batch (the reference sums the control
+    cost over the WHOLE batch, hopper.py:98 / half_cheetah.py:61), optional all-reduce of that one
+    double across ranks when the batch is sharded, pass 2 = the fused row kernel.
+    Returns (reward [B,1] or None, done bool[B,1] or None, came_from_numpy)."""
+    family = params.family
+    o, was_np = env._to_device(obs, env.dtype)
+    if o.dim() != 2 or o.shape[1] != _lib.lib.emei_family_obs_dim(family):
+        raise ValueError(f"obs must be [B,{_lib.lib.emei_family_obs_dim(family)}], got {tuple(o.shape)}")
+    b = o.shape[0]
+    needs_pre = family in (_lib.HOPPER, _lib.HALFCHEETAH)
+    p = sumsq = None
+    if needs_pre and want != "terminal":
+        if pre_obs is None or action is None:
+            raise TypeError("get_batch_reward of this env needs obs, pre_obs and action")
+        p, _ = env._to_device(pre_obs, env.dtype)
+        a, _ = env._to_device(action, env.dtype)
+        if tuple(p.shape) != tuple(o.shape) or a.shape[0] != b:
+            raise ValueError("obs / pre_obs / action batch shapes disagree")
+        sumsq = torch.empty(1, dtype=torch.float64, device=env.device)
+        env._call("emei_sumsq", a.data_ptr(), a.numel(), sumsq.data_ptr(), env._stream())
+        if getattr(env, "ctrl_cost_scope", "global") == "global":
+            from .dist import all_reduce_sum_
+
+            all_reduce_sum_(sumsq, group)
+    elif needs_pre:
+        # terminal only: reward inputs are not needed; feed harmless placeholders
+        p = o
+        sumsq = torch.zeros(1, dtype=torch.float64, device=env.device)
+    reward = torch.empty((b, 1), dtype=env.dtype, device=env.device)
+    done = torch.empty((b, 1), dtype=torch.uint8, device=env.device)
+    env._call(
+        "emei_reward_terminal",
+        o.data_ptr(), p.data_ptr() if p is not None else None, reward.data_ptr(), done.data_ptr(),
+        env.stats.data_ptr() if getattr(env, "accumulate_scoring_stats", False) else None,
+        sumsq.data_ptr() if sumsq is not None else None, b, ctypes.byref(params), env._stream(),
+    )
+    return reward, done.view(torch.bool), was_np

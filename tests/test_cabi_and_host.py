@@ -1,0 +1,174 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol include/emei_b200.h declares,
+argument validation returns the documented codes (no compute without a GPU), and the host-side
+mirror of the reference API behaves like emei/core.py + test/test_core.py."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import emei_b200 as E
+from emei_b200 import _lib
+from emei_b200.core import EmeiEnv
+from emei_b200.dist import shard_range
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    text = open(os.path.join(ROOT, "include", "emei_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(emei_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    syms = header_symbols()
+    assert len(syms) >= 20
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/emei_b200.h but not exported"
+    assert sorted(_lib.exported_symbols()) == syms  # the ctypes binding covers the whole header
+    assert _lib.lib.emei_version() == 100
+
+
+def test_struct_layouts_match_header():
+    # sizes the C side compiles to (doubles then int32s, natural alignment)
+    assert ctypes.sizeof(_lib.CartPoleParams) == 13 * 8 + 4 * 4
+    assert ctypes.sizeof(_lib.ChargedBallParams) == 5 * 8 + 2 * 4
+    assert ctypes.sizeof(_lib.ScoringParams) == 2 * 4 + 13 * 8
+
+
+def test_argument_validation_codes():
+    lib = _lib.lib
+    p = _lib.CartPoleParams()
+    p.freq_rate, p.dt, p.variant, p.action_kind = 1, 0.02, _lib.CARTPOLE_SWINGUP, 0
+    f = lib.emei_cartpole_step_f32
+    assert f(None, None, None, None, None, None, None, -1, ctypes.byref(p), None) == -4
+    assert f(None, None, None, None, None, None, None, 0, ctypes.byref(p), None) == 0  # empty batch: no-op
+    assert f(None, None, None, None, None, None, None, 8, None, None) == -1
+    assert f(None, None, None, None, None, None, None, 8, ctypes.byref(p), None) == -1  # null state
+    p.variant = 99
+    assert f(None, None, None, None, None, None, None, 8, ctypes.byref(p), None) == -2
+    p.variant, p.action_kind = _lib.CARTPOLE_SWINGUP, 7
+    assert f(None, None, None, None, None, None, None, 8, ctypes.byref(p), None) == -3
+    p.action_kind, p.freq_rate = 0, 0
+    assert f(None, None, None, None, None, None, None, 8, ctypes.byref(p), None) == -6
+    p.freq_rate = 1
+    buf = (ctypes.c_float * 64)()
+    addr = ctypes.addressof(buf)
+    mis = addr + 4 if addr % 16 == 0 else addr  # a deliberately misaligned (host) address: rejected before any launch
+    if mis % 16 != 0:
+        assert f(mis, mis, None, addr, addr, addr, None, 8, ctypes.byref(p), None) == -5
+    s = _lib.ScoringParams()
+    s.family = 42
+    assert lib.emei_reward_terminal_f64(None, None, None, None, None, None, 4, ctypes.byref(s), None) == -2
+    s.family, s.dt = _lib.HOPPER, 0.0
+    assert lib.emei_reward_terminal_f64(None, None, None, None, None, None, 4, ctypes.byref(s), None) == -6
+    assert lib.emei_snapshot_copy(None, None, -3, None) == -4
+    assert lib.emei_snapshot_copy(None, None, 0, None) == 0
+    assert b"16-byte" in lib.emei_error_string(-5)
+    assert [lib.emei_family_obs_dim(k) for k in (_lib.HOPPER, _lib.HALFCHEETAH, _lib.I2P_BOUNDARY_SWINGUP, _lib.CHARGED_BALL, 77)] == [12, 18, 6, 4, -1]
+    assert [lib.emei_family_action_dim(k) for k in (_lib.HOPPER, _lib.HALFCHEETAH, _lib.CARTPOLE_SWINGUP)] == [3, 6, 1]
+
+
+def test_env_params_name(golden):
+    """test/test_core.py:9-14."""
+    env = EmeiEnv(env_params={"a": 3, "b": 5, "d": 0.33, "c": "c"})
+    assert env.env_params_name == "a=3&b=5&c=c&d=0.33" == str(golden("core")["name_abcd"])
+    env = EmeiEnv(env_params=dict(freq_rate=1, real_time_scale=0.02))
+    assert env.env_params_name == "freq_rate=1&real_time_scale=0.02"
+    env = E.make("CartPoleSwingUp-v0", freq_rate=4, real_time_scale=0.01)
+    assert env.env_params_name == str(golden("core")["name_cartpole"])
+    assert E.make("BoundaryInvertedPendulumSwingUp-v0").env_params_name == str(golden("scoring")["ip_env_params_name"])
+
+
+def test_freeze_flag():
+    """test/test_core.py:17-23 on the bare base class, incl. the asserts of core.py:28,36."""
+    env = EmeiEnv(env_params=dict(freq_rate=1, time_step=0.02))
+    env.freeze()
+    assert env.frozen
+    with pytest.raises(AssertionError):
+        env.freeze()
+    env.unfreeze()
+    assert not env.frozen
+    with pytest.raises(AssertionError):
+        env.unfreeze()
+
+
+def test_abstract_methods_raise():
+    """core.py:175-193; test/test_envs/test_classic_control/test_cartpole.py:4-11."""
+    from emei_b200.envs.classic_control.cartpole import BaseCartPoleEnv
+
+    env = EmeiEnv(env_params={})
+    for fn in (lambda: env.get_batch_init_state(2), lambda: env.get_batch_reward(None), lambda: env.get_batch_terminal(None)):
+        with pytest.raises(NotImplementedError):
+            fn()
+    with pytest.raises(AssertionError):
+        env.get_batch_next_obs(None)  # not frozen
+    with pytest.raises(NotImplementedError):
+        BaseCartPoleEnv().reset()
+
+
+def test_registry_ids_and_spaces():
+    ids = set(E.registry)
+    for must in (
+        "CartPoleBalancing-v0", "CartPoleSwingUp-v0", "ContinuousCartPoleBalancing-v0", "ContinuousCartPoleSwingUp-v0",
+        "ChargedBallCentering-v0", "ContinuousChargedBallCentering-v0", "BoundaryInvertedPendulumSwingUp-v0",
+        "ReboundInvertedPendulumBalancing-v0", "BoundaryInvertedDoublePendulumSwingUp-v0", "HopperRunning-v0",
+        "HalfCheetahRunning-v0",
+    ):
+        assert must in ids
+    assert E.spec("CartPoleBalancing-v0")["max_episode_steps"] == 500
+    env = E.make("CartPoleSwingUp-v0", num_envs=3)
+    assert env.max_episode_steps == 1000 and env.action_space.n == 2 and env.observation_space.shape == (4,)
+    assert env.x_threshold == 5 and env.action_space.contains(1) and not env.action_space.contains(2)
+    env = E.make("ContinuousCartPoleSwingUp-v0")
+    assert env.action_space.shape == (1,) and env.action_space.contains(np.array([0.5], dtype=np.float32))
+    assert not env.action_space.contains(np.array([1.5], dtype=np.float32))
+    env = E.make("HopperRunning-v0")
+    assert env.observation_space.shape == (12,) and env.action_space.shape == (3,) and env.dt == 0.002 * 4
+    env = E.make("HalfCheetahRunning-v0", freq_rate=10, real_time_scale=0.002)
+    assert env.observation_space.shape == (18,) and env.action_space.shape == (6,) and abs(env.dt - 0.02) < 1e-15
+    env = E.make("ChargedBallCentering-v0", freq_rate=2)
+    assert env.env_params_name == "freq_rate=2&time_step=0.02" and env.time_step == 0.02
+    with pytest.raises(KeyError):
+        E.make("Walker2dRunning-v0")  # registered by the reference but its class does not exist there either
+    with pytest.raises(NotImplementedError):
+        E.make("HopperRunning-v0").step(np.zeros(3))  # MuJoCo dynamics are out of scope
+
+
+def test_transition_graphs(golden):
+    g = golden("scoring")
+    env = E.make("BoundaryInvertedPendulumSwingUp-v0")
+    for k in (1, 2, 3, 5):
+        assert np.array_equal(env.get_transition_graph(k), g[f"ip_graph_k{k}"])
+    assert env.get_reward_mech_graph() is None and env.get_termination_mech_graph() is None
+    with pytest.raises(AttributeError):
+        E.make("CartPoleSwingUp-v0").get_transition_graph()  # the reference has none (None.copy())
+    i2p = E.make("BoundaryInvertedDoublePendulumSwingUp-v0")
+    assert i2p.get_transition_graph().shape == (7, 6)
+
+
+def test_no_cpu_fallback():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    env = E.make("CartPoleSwingUp-v0", num_envs=4)
+    with pytest.raises(_lib.EmeiB200Error):
+        env.reset()
+    with pytest.raises(_lib.EmeiB200Error):
+        E.make("HopperRunning-v0").get_batch_terminal(np.ones((4, 12)))
+
+
+def test_shard_range_partitions_exactly():
+    for total in (0, 1, 7, 1 << 20, (1 << 26) + 5):
+        for w in (1, 2, 3, 4, 8):
+            parts = [shard_range(total, r, w) for r in range(w)]
+            assert parts[0][0] == 0 and parts[-1][1] == total
+            assert all(parts[i][1] == parts[i + 1][0] for i in range(w - 1))
+            sizes = [e - b for b, e in parts]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        shard_range(10, 3, 2)

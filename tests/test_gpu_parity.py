@@ -1,0 +1,648 @@
+"""GPU parity tests: the CUDA path (through the C ABI, via the env classes) against the CPU oracle
+and the golden vectors of the executed reference.
+
+Tolerances (BASELINE.json north_star):
+  * float64 mode: 1e-12 (relative to max(1,|value|)); terminal flags / done counts bit-exact;
+  * float32 mode: 1e-5 rel + 1e-6 abs per teacher-forced step; flags exact except where the state
+    lies within tolerance of a threshold.
+"""
+import warnings
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import emei_oracle as O
+from oracle import philox as P
+
+pytestmark = pytest.mark.gpu
+warnings.filterwarnings("ignore", category=RuntimeWarning)
+
+import emei_b200 as E  # noqa: E402
+from emei_b200.envs.classic_control import cartpole as CP  # noqa: E402
+from emei_b200.envs.classic_control import charged_ball as CB  # noqa: E402
+
+CARTPOLE = {
+    "balancing": CP.CartPoleBalancingEnv,
+    "swingup": CP.CartPoleSwingUpEnv,
+    "continuous_balancing": CP.ContinuousCartPoleBalancingEnv,
+    "continuous_swingup": CP.ContinuousCartPoleSwingUpEnv,
+}
+
+
+def close64(a, b, tol=1e-12):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    both_nan = np.isnan(a) & np.isnan(b)
+    same_inf = np.isinf(a) & (a == b)
+    return np.all(both_nan | same_inf | (np.abs(a - b) <= tol * np.maximum(1.0, np.abs(b))))
+
+
+def within32(a, ref, scale=1.0):
+    a, ref = np.asarray(a, dtype=np.float64), np.asarray(ref, dtype=np.float64)
+    return np.abs(a - ref) <= scale * (1e-6 + 1e-5 * np.abs(ref))
+
+
+# ================================================================================================
+# cart-pole step
+# ================================================================================================
+@pytest.mark.parametrize("kind", list(CARTPOLE))
+@pytest.mark.parametrize("fr", (1, 4))
+def test_cartpole_step_f64_vs_golden(golden, kind, fr):
+    g = golden("cartpole")
+    tag = f"{kind}_fr{fr}"
+    st, act = g[tag + "_state"], g[tag + "_action"]
+    env = CARTPOLE[kind](freq_rate=fr, num_envs=st.shape[0], dtype=torch.float64)
+    env.state = st
+    env.reset_stats()
+    obs, rew, done, trunc, info = env.step(act)
+    assert trunc is False and info == {}
+    assert obs.shape == (st.shape[0], 4) and rew.shape == (st.shape[0], 1) and done.shape == (st.shape[0], 1)
+    assert done.dtype == torch.bool and obs.dtype == torch.float64
+    obs, rew, done = obs.cpu().numpy(), rew.cpu().numpy(), done.cpu().numpy()
+    ref = g[tag + "_next"]
+    assert close64(obs, ref)
+    n_exact = int((obs == ref).all(axis=1).sum())
+    assert n_exact >= st.shape[0] - 1, f"only {n_exact}/{st.shape[0]} rows bit-identical"
+    assert close64(rew, g[tag + "_reward"])
+    assert np.array_equal(done, g[tag + "_done"])
+    rs, dc = env.read_stats()
+    assert dc == int(g[tag + "_done"].sum())
+    assert abs(rs - g[tag + "_reward"].sum()) <= 1e-9
+
+
+@pytest.mark.parametrize("kind", list(CARTPOLE))
+@pytest.mark.parametrize("fr", (1, 4))
+def test_cartpole_step_f32_vs_golden(golden, kind, fr):
+    g = golden("cartpole")
+    tag = f"{kind}_fr{fr}"
+    st, act = g[tag + "_state"], g[tag + "_action"]
+    env = CARTPOLE[kind](freq_rate=fr, num_envs=st.shape[0], dtype=torch.float32)
+    env.state = st  # cast to float32 by the engine
+    obs, rew, done, _, _ = env.step(act)
+    obs, rew, done = obs.cpu().numpy(), rew.cpu().numpy(), done.cpu().numpy()
+    ref = g[tag + "_next"]
+    small = np.abs(st[:, 2]) <= 4 * np.pi
+    ok = within32(obs, ref)
+    assert ok[small].all(), f"worst envelope fraction {(np.abs(obs - ref) / (1e-6 + 1e-5 * np.abs(ref)))[small].max()}"
+    # outside the working range the float32 quantisation of theta itself bounds the agreement
+    quant = np.spacing(np.abs(st[:, 2]).astype(np.float32)).astype(np.float64)[:, None] * 40.0 * 0.02 * fr
+    assert np.all(np.abs(obs - ref) <= (1e-6 + 1e-5 * np.abs(ref)) + quant)
+    assert within32(rew, g[tag + "_reward"]).all()
+    p = O.cartpole_params(kind)
+    near = (np.abs(np.abs(ref[:, 0]) - p.x_threshold) < 1e-4) | (np.abs(np.abs(ref[:, 2]) - p.theta_threshold_radians) < 1e-4)
+    assert np.array_equal(done[~near], g[tag + "_done"][~near])
+
+
+@pytest.mark.parametrize("kind", ("swingup", "continuous_swingup"))
+def test_cartpole_step_f32_identical_inputs_any_angle(golden, kind):
+    """Same float32 inputs on both sides (oracle in reference arithmetic): strict tolerance for ALL
+    angles, including the large unwrapped ones."""
+    g = golden("cartpole")
+    tag = f"{kind}_fr4"
+    st32 = g[tag + "_state"].astype(np.float32)
+    act = g[tag + "_action"]
+    p = O.cartpole_params(kind)
+    ref = O.cartpole_step_f64ref(st32.astype(np.float64), O.cartpole_force(act, kind.startswith("continuous"), p), 0.02, 4, p)
+    env = CARTPOLE[kind](freq_rate=4, num_envs=st32.shape[0], dtype=torch.float32)
+    env.state = st32
+    obs = env.step(act)[0].cpu().numpy()
+    frac = np.abs(obs - ref) / (1e-6 + 1e-5 * np.abs(ref))
+    assert frac.max() <= 1.0, f"worst envelope fraction {frac.max()}"
+
+
+def test_cartpole_free_running_trajectory_f64(golden):
+    """200 un-forced steps from the reference's reset(seed) states: float64 mode stays on the
+    reference trajectory (1e-12 per step compounds to < 1e-9 here; rows are normally bit-identical)."""
+    g = golden("cartpole")
+    acts, traj = g["traj_swingup_fr4_action"], g["traj_swingup_fr4"]
+    env = CP.CartPoleSwingUpEnv(freq_rate=4, num_envs=8, dtype=torch.float64)
+    env.state = g["traj_swingup_fr4_init"]
+    exact = 0
+    for t in range(acts.shape[1]):
+        obs, rew, done, _, _ = env.step(acts[:, t])
+        o = obs.cpu().numpy()
+        assert close64(o, traj[:, t, :4], 1e-9)
+        exact += int((o == traj[:, t, :4]).all())
+        assert close64(rew.cpu().numpy()[:, 0], traj[:, t, 4], 1e-9)
+        assert np.array_equal(done.cpu().numpy()[:, 0], traj[:, t, 5].astype(bool))
+    assert exact >= acts.shape[1] - 2, f"{exact}/{acts.shape[1]} steps bit-identical"
+
+
+def test_cartpole_teacher_forced_f32_trajectory(golden):
+    """The north-star protocol: reference states fed back every step, float32 engine."""
+    g = golden("cartpole")
+    acts, traj = g["traj_swingup_fr4_action"], g["traj_swingup_fr4"]
+    env = CP.CartPoleSwingUpEnv(freq_rate=4, num_envs=8, dtype=torch.float32)
+    prev = g["traj_swingup_fr4_init"]
+    worst = 0.0
+    for t in range(acts.shape[1]):
+        env.state = prev
+        obs = env.step(acts[:, t])[0].cpu().numpy()
+        ref = traj[:, t, :4]
+        worst = max(worst, (np.abs(obs - ref) / (1e-6 + 1e-5 * np.abs(ref))).max())
+        prev = ref
+    assert worst <= 1.0, f"worst envelope fraction {worst}"
+
+
+def test_cartpole_discrete_action_dtypes_and_int(golden):
+    g = golden("cartpole")
+    st, act = g["swingup_fr1_state"], g["swingup_fr1_action"]
+    outs = []
+    for dt in (torch.uint8, torch.int32, torch.int64):
+        env = CP.CartPoleSwingUpEnv(num_envs=st.shape[0], dtype=torch.float64)
+        env.state = st
+        outs.append(env.step(torch.as_tensor(act).to(dt))[0].cpu().numpy())
+    assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[1], outs[2])
+    env = CP.CartPoleSwingUpEnv(num_envs=1, dtype=torch.float64)
+    env.state = st[:1]
+    o = env.step(int(act[0]))[0].cpu().numpy()
+    assert np.array_equal(o, outs[0][:1])
+    with pytest.raises(AssertionError):
+        env.step(torch.tensor([0.5]))
+    env2 = CP.CartPoleSwingUpEnv(num_envs=1, dtype=torch.float64, validate_actions=True)
+    env2.state = st[:1]
+    with pytest.raises(AssertionError):
+        env2.step(torch.tensor([3]))
+    env3 = CP.CartPoleSwingUpEnv(num_envs=2)
+    with pytest.raises(AssertionError):
+        env3.step(torch.tensor([0, 1]))  # step before reset (base_control.py:67)
+
+
+def test_cartpole_reset_freeze_unfreeze_and_liveness():
+    """test/test_envs/test_classic_control/test_cartpole.py:14-35 (terminates eventually) +
+    test/test_core.py:17-23 (frozen flag) + snapshot/restore semantics."""
+    for cls in (CP.CartPoleBalancingEnv, CP.CartPoleSwingUpEnv):
+        env = cls(num_envs=64)
+        obs, info = env.reset(seed=1)
+        assert obs.shape == (64, 4) and info == {}
+        env.action_space.seed(0)
+        ever_done = torch.zeros(64, dtype=torch.bool, device=obs.device)
+        for _ in range(3000):
+            o, r, term, trunc, _ = env.step(env.action_space.sample_batch(64))
+            ever_done |= term[:, 0]
+            if bool(ever_done.all()):
+                break
+        assert bool(ever_done.all())
+    env = CP.CartPoleSwingUpEnv(num_envs=1000, freq_rate=2)
+    env.reset(seed=3)
+    a = env.action_space.sample_batch(1000)
+    env.step(a)
+    env.freeze()
+    assert env.frozen
+    s0 = env.state.clone()
+    o1 = env.step(a)[0].clone()
+    env.step(a)
+    env.unfreeze()
+    assert not env.frozen
+    assert torch.equal(env.state, s0)
+    assert torch.equal(env.step(a)[0], o1)  # deterministic replay from the snapshot
+    fresh = CP.CartPoleSwingUpEnv(num_envs=4)
+    with pytest.raises(RuntimeError):
+        fresh.unfreeze()
+
+
+def test_cartpole_init_state_philox_bit_exact_and_shard_invariant():
+    env = CP.CartPoleSwingUpEnv(num_envs=4096, dtype=torch.float64)
+    obs, _ = env.reset(seed=5)
+    seed0 = (5 * 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF
+    host = P.init_uniform(4096, 4, -0.05, 0.05, 2, seed0)
+    assert np.array_equal(obs.cpu().numpy(), host)
+    # shard [1024, 2048) of the same global batch
+    part = CP.CartPoleSwingUpEnv(num_envs=1024, dtype=torch.float64, env_offset=1024)
+    pobs, _ = part.reset(seed=5)
+    assert np.array_equal(pobs.cpu().numpy(), host[1024:2048])
+    # distribution vs the reference's sampler (golden): moments only
+    x = obs.cpu().numpy() - np.array([0, 0, np.pi, 0])
+    assert np.all(np.abs(x) <= 0.05)
+    assert np.allclose(x.mean(0), 0, atol=3e-3) and np.allclose(x.std(0), 0.1 / np.sqrt(12), atol=1e-3)
+    e32 = CP.CartPoleBalancingEnv(num_envs=4096, dtype=torch.float32)
+    o32, _ = e32.reset(seed=5)
+    assert np.array_equal(o32.cpu().numpy(), P.init_uniform(4096, 4, -0.05, 0.05, -1, seed0, dtype=np.float32))
+    o32b, _ = e32.reset()  # second reset draws a fresh stream
+    assert not torch.equal(o32, o32b)
+
+
+def test_cartpole_get_batch_api_numpy_roundtrip(golden):
+    g = golden("cartpole")
+    for kind in ("balancing", "swingup"):
+        tag = f"{kind}_fr1"
+        env = CARTPOLE[kind](dtype=torch.float64)
+        nxt = g[tag + "_next"]
+        r = env.get_batch_reward(nxt)
+        d = env.get_batch_terminal(nxt)
+        assert isinstance(r, np.ndarray) and r.shape == (nxt.shape[0], 1) and d.dtype == np.bool_
+        assert close64(r, g[tag + "_reward"]) and np.array_equal(d, g[tag + "_done"])
+        rt, dt = env.get_batch_reward(torch.as_tensor(nxt)), env.get_batch_terminal(torch.as_tensor(nxt))
+        assert isinstance(rt, torch.Tensor) and rt.is_cuda and dt.dtype == torch.bool
+    # get_batch_next_obs: needs frozen (core.py:190-193); stateless one-step dynamics
+    env = CP.CartPoleSwingUpEnv(freq_rate=4, dtype=torch.float64, num_envs=3)
+    with pytest.raises(AssertionError):
+        env.get_batch_next_obs(g["swingup_fr4_state"], action=g["swingup_fr4_action"])
+    env.reset(seed=0)
+    env.freeze()
+    s_before = env.state.clone()
+    nxt = env.get_batch_next_obs(g["swingup_fr4_state"], action=g["swingup_fr4_action"])
+    assert close64(nxt, g["swingup_fr4_next"])
+    assert torch.equal(env.state, s_before)
+
+
+# ================================================================================================
+# analytic inverted pendulum
+# ================================================================================================
+IP = {
+    "ip_rebound_balancing": "ReboundInvertedPendulumBalancing-v0",
+    "ip_boundary_balancing": "BoundaryInvertedPendulumBalancing-v0",
+    "ip_rebound_swingup": "ReboundInvertedPendulumSwingUp-v0",
+    "ip_boundary_swingup": "BoundaryInvertedPendulumSwingUp-v0",
+}
+
+
+def ip_inputs(seed, n):
+    rng = np.random.default_rng(seed)
+    st = rng.uniform(-1, 1, size=(n, 4)) * np.array([1.9, np.pi, 5.0, 8.0])
+    st[: n // 8, 1] *= 30.0  # unwrapped angles
+    st[n // 8 : n // 4, 0] = np.sign(st[n // 8 : n // 4, 0]) * rng.uniform(1.95, 2.05, n // 4 - n // 8)
+    act = rng.uniform(-3.5, 3.5, size=(n, 1)).astype(np.float32)  # beyond ctrlrange: clamped like mj_step
+    return st, act
+
+
+@pytest.mark.parametrize("kind", list(IP))
+@pytest.mark.parametrize("fr", (1, 3))
+def test_ip_step_f64_vs_oracle(kind, fr):
+    st, act = ip_inputs(1001, 4096)
+    p = O.InvertedPendulumParams()
+    ctrl = np.clip(act.astype(np.float64), p.ctrl_low, p.ctrl_high)
+    ref_state, ref_obs = O.ip_step(st, ctrl, 0.02, fr, kind.endswith("swingup"), p, libm=True)
+    env = E.make(IP[kind], freq_rate=fr, num_envs=4096, dtype=torch.float64)
+    env.state = st
+    obs, rew, done, _, _ = env.step(act)
+    assert close64(env.state.cpu().numpy(), ref_state)
+    o = obs.cpu().numpy()
+    # wrapped angle: compare on the circle (a 1-ulp state difference can land on the other side of +-pi)
+    dth = np.abs((o[:, 1] - ref_obs[:, 1] + np.pi) % (2 * np.pi) - np.pi)
+    assert dth.max() <= 1e-12 and close64(o[:, [0, 2, 3]], ref_obs[:, [0, 2, 3]])
+    assert np.all((o[:, 1] >= -np.pi) & (o[:, 1] < np.pi))
+    assert close64(rew.cpu().numpy(), O.ip_reward(kind, ref_obs), 1e-11)
+    ref_done = O.ip_terminal(kind, ref_obs, p)
+    near = (np.abs(np.abs(ref_obs[:, 0]) - 2.0) < 1e-9) | (np.abs(np.cos(ref_obs[:, 1]) - 0.9) < 1e-9) | (np.abs(np.cos(ref_obs[:, 1])) < 1e-9)
+    assert np.array_equal(done.cpu().numpy()[~near], ref_done[~near])
+    assert 0 < ref_done.mean() < 1 or kind == "ip_rebound_swingup"
+
+
+@pytest.mark.parametrize("kind", ("ip_boundary_swingup", "ip_boundary_balancing"))
+def test_ip_step_f32_vs_oracle_identical_inputs(kind):
+    st, act = ip_inputs(1002, 4096)
+    st32 = st.astype(np.float32)
+    p = O.InvertedPendulumParams()
+    ctrl = np.clip(act.astype(np.float64), p.ctrl_low, p.ctrl_high)
+    ref_state, ref_obs = O.ip_step(st32.astype(np.float64), ctrl, 0.02, 1, kind.endswith("swingup"), p)
+    env = E.make(IP[kind], num_envs=4096, dtype=torch.float32)
+    env.state = st32
+    obs, rew, done, _, _ = env.step(act)
+    assert within32(env.state.cpu().numpy(), ref_state).all()
+    o = obs.cpu().numpy().astype(np.float64)
+    dth = np.abs((o[:, 1] - ref_obs[:, 1] + np.pi) % (2 * np.pi) - np.pi)
+    assert np.all(dth <= 1e-6 + 1e-5 * np.abs(ref_state[:, 1]))
+    assert within32(rew.cpu().numpy(), O.ip_reward(kind, ref_obs), 2.0).all()
+    ref_done = O.ip_terminal(kind, ref_obs, p)
+    near = (np.abs(np.abs(ref_obs[:, 0]) - 2.0) < 1e-4) | (np.abs(np.cos(ref_obs[:, 1])) < 1e-4)
+    assert np.array_equal(done.cpu().numpy()[~near], ref_done[~near])
+
+
+def test_ip_reset_liveness_graph():
+    """test/test_envs/test_mujoco/test_inverted_pendulum.py:14-62: Boundary variants and Rebound
+    Balancing terminate eventually; Rebound SwingUp never terminates within 100 steps."""
+    for kind, must_end in (("ip_boundary_swingup", True), ("ip_boundary_balancing", True), ("ip_rebound_balancing", True)):
+        env = E.make(IP[kind], num_envs=32)
+        obs, _ = env.reset(seed=2)
+        assert obs.shape == (32, 4) and float(obs.abs().max()) < 0.05
+        env.action_space.seed(1)
+        ever = torch.zeros(32, dtype=torch.bool, device=obs.device)
+        for _ in range(5000):
+            ever |= env.step(env.action_space.sample_batch(32))[2][:, 0]
+            if bool(ever.all()):
+                break
+        assert bool(ever.all()) == must_end
+    env = E.make(IP["ip_rebound_swingup"], num_envs=32)
+    env.reset(seed=2)
+    for _ in range(101):
+        assert not bool(env.step(env.action_space.sample_batch(32))[2].any())
+    assert env.get_transition_graph().shape == (5, 4)
+
+
+# ================================================================================================
+# charged ball
+# ================================================================================================
+@pytest.mark.parametrize("tag", ("disc_fr1", "disc_fr3", "cont_fr1", "cont_fr3"))
+def test_charged_ball_f64_teacher_forced_vs_golden(golden, tag):
+    c = golden("charged_ball")
+    fr, cont = int(tag[-1]), tag.startswith("cont")
+    on, ci, fre, act = c[tag + "_on"], c[tag + "_circle"], c[tag + "_free"], c[tag + "_action"]
+    T, n = act.shape[0], on.shape[1]
+    # all T teacher-forced steps in ONE batch of T*n envs
+    cls = CB.ContinuousChargedBallCenteringEnv if cont else CB.ChargedBallCenteringEnv
+    env = cls(freq_rate=fr, num_envs=T * n, dtype=torch.float64)
+    env.state = dict(on_circle=on[:-1].reshape(-1).astype(np.uint8), circle_state=ci[:-1].reshape(-1, 2), free_state=fre[:-1].reshape(-1, 4))
+    a = act.reshape(T * n, 1) if cont else act.reshape(-1)
+    obs, rew, done, _, _ = env.step(a)
+    st = env.state
+    got_on = st["on_circle"].cpu().numpy().astype(bool)
+    ref_on = on[1:].reshape(-1)
+    assert np.array_equal(got_on, ref_on)
+    assert close64(st["free_state"].cpu().numpy(), fre[1:].reshape(-1, 4))
+    # circle state is meaningful while on the circle (it is stale, but still carried, in flight)
+    assert close64(st["circle_state"].cpu().numpy(), ci[1:].reshape(-1, 2), 1e-11)
+    assert torch.equal(obs, st["free_state"])
+    ref_rew = O.charged_ball_reward(fre[1:].reshape(-1, 4), O.ChargedBallParams())
+    assert close64(rew.cpu().numpy(), ref_rew)
+    assert not bool(done.any())
+
+
+@pytest.mark.parametrize("tag", ("disc_fr1", "cont_fr3"))
+def test_charged_ball_f32_teacher_forced(golden, tag):
+    c = golden("charged_ball")
+    fr, cont = int(tag[-1]), tag.startswith("cont")
+    on, ci, fre, act = c[tag + "_on"], c[tag + "_circle"], c[tag + "_free"], c[tag + "_action"]
+    T, n = act.shape[0], on.shape[1]
+    on0 = on[:-1].reshape(-1)
+    ci32, fr32 = ci[:-1].reshape(-1, 2).astype(np.float32), fre[:-1].reshape(-1, 4).astype(np.float32)
+    p = O.ChargedBallParams()
+    a = act.reshape(T * n, 1) if cont else act.reshape(-1)
+    Ef = O.charged_ball_force(a, cont, p)
+    r_on, r_ci, r_fr = O.charged_ball_step(on0, ci32.astype(np.float64), fr32.astype(np.float64), Ef, fr, p, f32_force=cont)
+    cls = CB.ContinuousChargedBallCenteringEnv if cont else CB.ChargedBallCenteringEnv
+    env = cls(freq_rate=fr, num_envs=T * n, dtype=torch.float32)
+    env.state = dict(on_circle=on0.astype(np.uint8), circle_state=ci32, free_state=fr32)
+    env.step(a)
+    st = env.state
+    got_on = st["on_circle"].cpu().numpy().astype(bool)
+    agree = got_on == r_on
+    assert agree.mean() > 0.995  # regime flags may flip only at the take-off / landing thresholds
+    # landing re-derives (theta, omega) from asin near |arg| = 1 where float32 loses half its digits:
+    # compare positions/velocities everywhere, and a looser bound on rows that just landed
+    landed = r_on & ~on0
+    ok = within32(st["free_state"].cpu().numpy(), r_fr, 4.0).all(axis=1)
+    assert ok[agree & ~landed].all()
+    okc = within32(st["circle_state"].cpu().numpy(), r_ci, 4.0).all(axis=1)
+    assert okc[agree & on0 & r_on].all()
+
+
+def test_charged_ball_reset_and_rollout_stats():
+    env = CB.ChargedBallCenteringEnv(num_envs=2048, dtype=torch.float64)
+    obs, _ = env.reset(seed=9)
+    seed0 = (9 * 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF
+    h_on, h_ci, h_fr = P.init_charged_ball(2048, 1.0, seed0)
+    st = env.state
+    assert np.array_equal(st["on_circle"].cpu().numpy(), h_on)
+    assert np.array_equal(st["circle_state"].cpu().numpy(), h_ci)
+    assert close64(st["free_state"].cpu().numpy(), h_fr, 1e-15)
+    # 50-step rollout vs oracle, un-forced, float64
+    p = O.ChargedBallParams()
+    rng = np.random.default_rng(0)
+    on, ci, fre = h_on.astype(bool), h_ci, st["free_state"].cpu().numpy()
+    env.reset_stats()
+    total = 0.0
+    for t in range(50):
+        a = rng.integers(0, 2, size=2048)
+        obs, rew, done, _, _ = env.step(a)
+        on, ci, fre = O.charged_ball_step(on, ci, fre, O.charged_ball_force(a, False, p), 1, p)
+        total += O.charged_ball_reward(fre, p).sum()
+    assert np.array_equal(env.state["on_circle"].cpu().numpy().astype(bool), on)
+    assert close64(obs.cpu().numpy(), fre, 1e-9)
+    rs, dc = env.read_stats()
+    assert dc == 0 and abs(rs - total) < 1e-6 * abs(total)
+    # freeze / unfreeze restores all three arrays
+    env.freeze()
+    snap = {k: v.clone() for k, v in env.state.items()}
+    env.step(rng.integers(0, 2, size=2048))
+    env.unfreeze()
+    for k in snap:
+        assert torch.equal(env.state[k], snap[k])
+
+
+# ================================================================================================
+# scoring (get_batch_reward / get_batch_terminal)
+# ================================================================================================
+def test_hopper_scoring_f64_vs_golden(golden):
+    g = golden("scoring")
+    for T in (1, 0):
+        tag = f"hopper_T{T}"
+        env = E.make("HopperRunning-v0", terminate_when_unhealthy=bool(T), dtype=torch.float64)
+        assert env.dt == float(g[tag + "_dt"])
+        obs, pre, act = g[tag + "_obs"], g[tag + "_pre_obs"], g[tag + "_action"]
+        r = env.get_batch_reward(obs, pre, act)
+        d = env.get_batch_terminal(obs, pre, act)
+        assert r.shape == (obs.shape[0], 1) and d.shape == (obs.shape[0], 1) and d.dtype == np.bool_
+        assert close64(r, g[tag + "_reward"]) and np.array_equal(d, g[tag + "_done"])
+        assert np.array_equal(env.is_healthy(obs), g[tag + "_healthy"])
+        r2, d2 = env.get_batch_reward_terminal(obs, pre, act)
+        assert np.array_equal(r2, r, equal_nan=True) and np.array_equal(d2, d)
+    # the reference's own known-answer test (test_hopper.py:6-25)
+    env = E.make("HopperRunning-v0", dtype=torch.float64)
+    assert env.is_healthy(np.ones([128, 12])).shape == (128,) and np.all(env.is_healthy(np.ones([128, 12])))
+    assert not np.any(env.is_healthy(np.ones([128, 12]) * 101))
+    r = env.get_batch_reward(obs=np.ones([128, 12]), pre_obs=np.ones([128, 12]), action=np.ones([128, 3]))
+    assert r.shape == (128, 1) and close64(r, g["hopper_kat_reward"])
+    assert env.get_batch_terminal(obs=np.ones([128, 12])).shape == (128, 1)
+    # non-default constructor arguments
+    env = E.make(
+        "HopperRunning-v0", freq_rate=2, real_time_scale=0.01, forward_reward_weight=1.5, ctrl_cost_weight=2e-3,
+        healthy_reward=0.5, terminate_when_unhealthy=False, healthy_state_range=(-50.0, 60.0), healthy_z_range=(0.8, 2.0),
+        dtype=torch.float64,
+    )
+    obs, pre, act = g["hopper_custom_obs"], g["hopper_custom_pre_obs"], g["hopper_custom_action"]
+    assert close64(env.get_batch_reward(obs, pre, act), g["hopper_custom_reward"])
+    assert np.array_equal(env.get_batch_terminal(obs), g["hopper_custom_done"])
+
+
+def test_halfcheetah_scoring_f64_vs_golden(golden):
+    g = golden("scoring")
+    env = E.make("HalfCheetahRunning-v0", dtype=torch.float64)
+    obs, pre, act = g["halfcheetah_obs"], g["halfcheetah_pre_obs"], g["halfcheetah_action"]
+    assert close64(env.get_batch_reward(obs, pre, act), g["halfcheetah_reward"])
+    assert np.array_equal(env.get_batch_terminal(obs, pre, act), g["halfcheetah_done"])
+
+
+@pytest.mark.parametrize("name", ("hopper", "halfcheetah"))
+def test_mujoco_scoring_f32_identical_inputs(golden, name):
+    g = golden("scoring")
+    tag = "hopper_T0" if name == "hopper" else "halfcheetah"
+    obs, pre, act = (g[tag + s].astype(np.float32) for s in ("_obs", "_pre_obs", "_action"))
+    if name == "hopper":
+        env = E.make("HopperRunning-v0", terminate_when_unhealthy=False, dtype=torch.float32)
+        p = O.HopperParams(terminate_when_unhealthy=False)
+        ref_r = O.hopper_reward(obs.astype(np.float64), pre.astype(np.float64), act.astype(np.float64), p)
+        ref_d = O.hopper_terminal(obs.astype(np.float64), p)
+    else:
+        env = E.make("HalfCheetahRunning-v0", dtype=torch.float32)
+        p = O.HalfCheetahParams()
+        ref_r = O.halfcheetah_reward(obs.astype(np.float64), pre.astype(np.float64), act.astype(np.float64), p)
+        ref_d = O.halfcheetah_terminal(obs.astype(np.float64))
+    r, d = env.get_batch_reward_terminal(obs, pre, act)
+    fin = np.isfinite(ref_r)
+    # the batch-wide control cost (hundreds) is subtracted from an O(1) term: compare at the
+    # magnitude of the operands, which is what float32 arithmetic can resolve
+    cc = p.ctrl_cost_weight * float(np.sum(np.square(act.astype(np.float64))))
+    assert np.all(np.abs(r.astype(np.float64) - ref_r)[fin] <= 1e-6 + 1e-5 * (np.abs(ref_r[fin]) + cc))
+    assert np.array_equal(np.isnan(r), np.isnan(ref_r))
+    assert np.array_equal(d, ref_d)
+
+
+@pytest.mark.parametrize(
+    "kind",
+    list(IP) + ["i2p_rebound_balancing", "i2p_boundary_balancing", "i2p_rebound_swingup", "i2p_boundary_swingup"],
+)
+def test_pendulum_scoring_vs_golden(golden, kind):
+    g = golden("scoring")
+    ids = dict(IP)
+    ids.update({k: k.replace("i2p_", "").title().replace("_", "") for k in ()})
+    name = {
+        "i2p_rebound_balancing": "ReboundInvertedDoublePendulumBalancing-v0",
+        "i2p_boundary_balancing": "BoundaryInvertedDoublePendulumBalancing-v0",
+        "i2p_rebound_swingup": "ReboundInvertedDoublePendulumSwingUp-v0",
+        "i2p_boundary_swingup": "BoundaryInvertedDoublePendulumSwingUp-v0",
+        **IP,
+    }[kind]
+    obs = g[kind + "_obs"]
+    env = E.make(name, dtype=torch.float64)
+    assert close64(env.get_batch_reward(obs), g[kind + "_reward"])
+    assert np.array_equal(env.get_batch_terminal(obs), g[kind + "_done"])
+    env32 = E.make(name, dtype=torch.float32)
+    o32 = obs.astype(np.float32)
+    r32, d32 = env32.get_batch_reward_terminal(o32)
+    if kind.startswith("ip"):
+        ref_r, ref_d = O.ip_reward(kind, o32.astype(np.float64)), O.ip_terminal(kind, o32.astype(np.float64))
+    else:
+        ref_r, ref_d = O.i2p_reward(kind, o32.astype(np.float64)), O.i2p_terminal(kind, o32.astype(np.float64))
+    fin = np.isfinite(ref_r)
+    assert within32(r32[fin], ref_r[fin], 2.0).all()
+    assert (d32 == ref_d).mean() > 0.99
+
+
+def test_mujoco_init_obs_distribution_and_philox():
+    for name, d, mean, sigma in (
+        ("HopperRunning-v0", 12, [0, 1.25] + [0] * 10, 5e-3),
+        ("HalfCheetahRunning-v0", 18, [0] * 18, 0.1),
+        ("BoundaryInvertedPendulumSwingUp-v0", 4, [0] * 4, 5e-3),
+    ):
+        env = E.make(name, dtype=torch.float64)
+        env._reseed(11)
+        obs = env.get_batch_init_obs(8192)
+        assert obs.shape == (8192, d)
+        seed0 = (11 * 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF
+        host = P.init_gaussian(8192, d, np.array(mean, dtype=np.float64), np.full(d, sigma), seed0)
+        assert np.allclose(obs.cpu().numpy(), host, rtol=0, atol=1e-12 * max(1.0, sigma * 10))
+        x = obs.cpu().numpy() - np.array(mean)
+        assert np.allclose(x.mean(0), 0, atol=5 * sigma / np.sqrt(8192)) and np.allclose(x.std(0), sigma, rtol=0.05)
+        pos, vel = env.get_batch_init_state(16)
+        assert pos.shape == (16, d // 2) and vel.shape == (16, d // 2)
+        assert env.transform_state_to_obs((pos, vel)).shape == (16, d)
+        p2, v2 = env.transform_obs_to_state(obs)
+        assert p2.shape[1] == d // 2 and v2.shape[1] == d // 2
+    env = E.make("HopperRunning-v0", init_noise_params=(0.0, 0.2), dtype=torch.float64)
+    o = env.get_batch_init_obs(4096).cpu().numpy()
+    assert np.all(o[:, :6] == np.array([0, 1.25, 0, 0, 0, 0])) and abs(o[:, 6:].std() - 0.2) < 0.01
+    env = E.make("HopperRunning-v0", init_noise_params={1: (0.3, 0.0)}, dtype=torch.float64)
+    o = env.get_batch_init_obs(4096).cpu().numpy()
+    assert abs(o[:, 1].std() - 0.3) < 0.02 and np.all(o[:, 2:] == 0)
+
+
+# ================================================================================================
+# BASELINE.json full sizes: size-independent properties + strided oracle subsample
+# ================================================================================================
+def test_c2_full_size_properties():
+    """C2: ContinuousCartPoleSwingUp, 2^20 envs, freq_rate=4."""
+    n = 1 << 20
+    rng = np.random.default_rng(1002)
+    st = (rng.uniform(-1, 1, size=(n, 4)) * np.array([4.0, 5.0, np.pi, 8.0])).astype(np.float32)
+    k = n // 100
+    st[:k, 0] = np.sign(st[:k, 0]) * rng.uniform(4.99, 5.01, size=k).astype(np.float32)
+    act = rng.uniform(-1, 1, size=(n, 1)).astype(np.float32)
+    env = CP.ContinuousCartPoleSwingUpEnv(freq_rate=4, num_envs=n, dtype=torch.float32)
+    env.state = st
+    env.reset_stats()
+    obs, rew, done, _, _ = env.step(act)
+    # statistics reductions == reductions of the outputs
+    rs, dc = env.read_stats()
+    assert dc == int(done.sum())
+    assert abs(rs - float(rew.double().sum())) < 1e-6 * n
+    # strided subsample against the reference-arithmetic oracle
+    idx = np.arange(0, n, 16)
+    p = O.cartpole_params("continuous_swingup")
+    ref = O.cartpole_step_f64ref(st[idx].astype(np.float64), O.cartpole_force(act[idx], True, p), 0.02, 4, p, libm=False)
+    o = obs.cpu().numpy()[idx]
+    frac = np.abs(o - ref) / (1e-6 + 1e-5 * np.abs(ref))
+    assert frac.max() <= 1.0, f"worst envelope fraction {frac.max()}"
+    near = np.abs(np.abs(ref[:, 0]) - 5.0) < 1e-4
+    assert np.array_equal(done.cpu().numpy()[idx][~near], O.cartpole_terminal("swingup", ref, p)[~near])
+    # idempotence of freeze/unfreeze and determinism of the kernel
+    env.freeze()
+    o2 = env.step(act)[0].clone()
+    env.unfreeze()
+    assert torch.equal(env.step(act)[0], o2)
+
+
+def test_c3_full_size_properties():
+    """C3: Hopper / HalfCheetah reward+terminal on 2^24 synthetic transitions (float32)."""
+    n = 1 << 24
+    dev = torch.device("cuda")
+    gen = torch.Generator(device=dev).manual_seed(1003)
+    for name, d, a_dim in (("HopperRunning-v0", 12, 3), ("HalfCheetahRunning-v0", 18, 6)):
+        kw = dict(terminate_when_unhealthy=False) if d == 12 else {}
+        env = E.make(name, dtype=torch.float32, **kw)
+        env.accumulate_scoring_stats = True
+        obs = torch.randn((n, d), device=dev, generator=gen)
+        if d == 12:
+            obs[:, 1] = 1.25 + 0.4 * obs[:, 1]
+            obs[:, 2:] *= 30.0
+        bad = torch.randint(0, n, (n // 1000,), device=dev, generator=gen)
+        obs[bad, 3] = float("nan")
+        pre = obs.clone()
+        pre[:, 0] -= 0.01 * torch.randn(n, device=dev, generator=gen)
+        act = torch.rand((n, a_dim), device=dev, generator=gen) * 2 - 1
+        env.reset_stats()
+        r, dn = env.get_batch_reward_terminal(obs, pre, act)
+        rs, dc = env.read_stats()
+        assert dc == int(dn.sum())
+        assert int(dn.sum()) >= len(torch.unique(bad))
+        # subsample vs oracle with the batch-wide control cost taken from the full batch
+        idx = torch.arange(0, n, 256, device=dev)
+        sumsq = float((act.double() ** 2).sum())
+        o, p_, a = obs[idx].cpu().numpy().astype(np.float64), pre[idx].cpu().numpy().astype(np.float64), act[idx].cpu().numpy().astype(np.float64)
+        if d == 12:
+            P_ = O.HopperParams(terminate_when_unhealthy=False)
+            ref_r, ref_d = O.hopper_reward(o, p_, a, P_, sumsq=sumsq), O.hopper_terminal(o, P_)
+        else:
+            P_ = O.HalfCheetahParams()
+            ref_r, ref_d = O.halfcheetah_reward(o, p_, a, P_, sumsq=sumsq), O.halfcheetah_terminal(o)
+        rr = r[idx].cpu().numpy().astype(np.float64)
+        fin = np.isfinite(ref_r)
+        cc = P_.ctrl_cost_weight * sumsq
+        assert np.all(np.abs(rr - ref_r)[fin] <= 1e-6 + 1e-5 * (np.abs(ref_r[fin]) + cc))
+        assert np.array_equal(dn[idx].cpu().numpy(), ref_d)
+        del obs, pre, act, r, dn
+        torch.cuda.empty_cache()
+
+
+def test_empty_and_ragged_batches():
+    from emei_b200 import _lib
+
+    # n = 0 is a valid no-op at the C ABI
+    p = _lib.CartPoleParams()
+    p.freq_rate, p.dt, p.variant = 1, 0.02, _lib.CARTPOLE_SWINGUP
+    import ctypes
+
+    assert _lib.lib.emei_cartpole_step_f32(None, None, None, None, None, None, None, 0, ctypes.byref(p), None) == 0
+    # ragged sizes (not multiples of the CTA / vector width)
+    for n in (1, 31, 257, 1000003):
+        env = CP.CartPoleSwingUpEnv(num_envs=n, freq_rate=2)
+        env.reset(seed=n)
+        env.reset_stats()
+        o, r, d, _, _ = env.step(env.action_space.sample_batch(n))
+        assert o.shape == (n, 4) and torch.isfinite(o).all()
+        rs, dc = env.read_stats()
+        assert abs(rs - float(r.double().sum())) < 1e-6 * n and dc == int(d.sum())
+    env = E.make("HalfCheetahRunning-v0", dtype=torch.float64)
+    for n in (1, 5, 1025):
+        r, d = env.get_batch_reward_terminal(np.zeros((n, 18)), np.zeros((n, 18)), np.ones((n, 6)))
+        assert r.shape == (n, 1) and close64(r, np.full((n, 1), -0.1 * 6 * n))
