@@ -259,3 +259,35 @@ def score(env, params: _lib.ScoringParams, obs, pre_obs=None, action=None, want=
         sumsq.data_ptr() if sumsq is not None else None, b, ctypes.byref(params), env._stream(),
     )
     return reward, done.view(torch.bool), was_np
+
+
+class HostStaging:
+    """Pinned host buffers + the copy choreography of ``step_host`` (end-to-end path with HOST inputs
+    and outputs).  Works for any env whose ``step`` returns ``(obs, reward, done)`` device tensors."""
+
+    def __init__(self, env):
+        self.env = env
+        n = env.num_envs
+        cont = len(env.action_space.shape) > 0
+        self.a_host = torch.empty((n,), dtype=torch.float32 if cont else torch.uint8).pin_memory()
+        self.a_dev = torch.empty_like(self.a_host, device=env.device)
+        obs_dim = env.observation_space.shape[0]
+        self.obs_host = torch.empty((n, obs_dim), dtype=env.dtype).pin_memory()
+        self.rew_host = torch.empty((n, 1), dtype=env.dtype).pin_memory()
+        self.done_host = torch.empty((n, 1), dtype=torch.bool).pin_memory()
+        self.h2d_bytes = self.a_host.numel() * self.a_host.element_size()
+        self.d2h_bytes = sum(t.numel() * t.element_size() for t in (self.obs_host, self.rew_host, self.done_host))
+
+    def step(self, action):
+        env = self.env
+        a = torch.as_tensor(action)
+        if a.is_cuda:
+            raise TypeError("step_host takes host actions; use step() for device tensors")
+        self.a_host.copy_(a.reshape(-1))  # host-side cast into the pinned staging buffer (uint8 / float32)
+        self.a_dev.copy_(self.a_host, non_blocking=True)
+        obs, reward, done, trunc, info = env.step(self.a_dev)
+        self.obs_host.copy_(obs, non_blocking=True)
+        self.rew_host.copy_(reward, non_blocking=True)
+        self.done_host.copy_(done, non_blocking=True)
+        torch.cuda.current_stream(env.device).synchronize()
+        return self.obs_host.numpy(), self.rew_host.numpy(), self.done_host.numpy(), trunc, info

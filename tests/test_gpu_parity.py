@@ -87,7 +87,8 @@ def test_cartpole_step_f32_vs_golden(golden, kind, fr):
     # outside the working range the float32 quantisation of theta itself bounds the agreement
     quant = np.spacing(np.abs(st[:, 2]).astype(np.float32)).astype(np.float64)[:, None] * 40.0 * 0.02 * fr
     assert np.all(np.abs(obs - ref) <= (1e-6 + 1e-5 * np.abs(ref)) + quant)
-    assert within32(rew, g[tag + "_reward"]).all()
+    ok_r = np.abs(rew - g[tag + "_reward"]) <= 1e-6 + 1e-5 * np.abs(g[tag + "_reward"]) + quant  # cos(theta): same theta quantisation
+    assert ok_r.all() and within32(rew, g[tag + "_reward"])[small].all()
     p = O.cartpole_params(kind)
     near = (np.abs(np.abs(ref[:, 0]) - p.x_threshold) < 1e-4) | (np.abs(np.abs(ref[:, 2]) - p.theta_threshold_radians) < 1e-4)
     assert np.array_equal(done[~near], g[tag + "_done"][~near])
