@@ -25,6 +25,14 @@ inline int grid_for(int64_t n, int per_block) {
   return static_cast<int>(g);
 }
 
+// persistent launch: enough CTAs to cover n once, capped at ctas_per_sm resident CTAs on every SM
+// (the kernels grid-stride over the rest, so every SM carries the same number of units +-1)
+inline int persistent_grid(int64_t n, int per_block, int ctas_per_sm) {
+  const int64_t want = (n + per_block - 1) / per_block;
+  const int64_t cap = static_cast<int64_t>(kNumSMs) * ctas_per_sm;
+  return static_cast<int>(want < 1 ? 1 : (want > cap ? cap : want));
+}
+
 // ---------------------------------------------------------------------------------------------
 // vector types: one env row (4 scalars) per 128-bit (f32) / 2 x 128-bit (f64) access
 // ---------------------------------------------------------------------------------------------
@@ -119,6 +127,33 @@ __device__ __forceinline__ void block_stats_accumulate(double* stats, double rew
     rr = warp_sum(rr);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) dd += __shfl_xor_sync(0xffffffffu, dd, o);
+    if (lane == 0) {
+      atomicAdd(&stats[0], rr);
+      atomicAdd(&stats[1], static_cast<double>(dd));  // exact: counts << 2^53
+    }
+  }
+}
+
+// Same, for kernels whose threads carry several units: per-thread reward partial + done COUNT.
+// Must be called by ALL threads of the CTA.
+__device__ __forceinline__ void block_stats_accumulate_counts(double* stats, double reward_sum, unsigned done_count) {
+  if (stats == nullptr) return;  // uniform across the grid
+  __shared__ double s_r2[kBlock / 32];
+  __shared__ unsigned s_d2[kBlock / 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const double r = warp_sum(reward_sum);
+  const unsigned d = __reduce_add_sync(0xffffffffu, done_count);
+  if (lane == 0) {
+    s_r2[warp] = r;
+    s_d2[warp] = d;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    const int nw = blockDim.x >> 5;
+    double rr = lane < nw ? s_r2[lane] : 0.0;
+    unsigned dd = lane < nw ? s_d2[lane] : 0u;
+    rr = warp_sum(rr);
+    dd = __reduce_add_sync(0xffffffffu, dd);
     if (lane == 0) {
       atomicAdd(&stats[0], rr);
       atomicAdd(&stats[1], static_cast<double>(dd));  // exact: counts << 2^53

@@ -170,9 +170,15 @@ int cartpole_step(const R* state_in, R* state_out, R* obs_out, const void* actio
   EMEI_CHECK_ALIGN16(state_in);
   EMEI_CHECK_ALIGN16(state_out);
   if (obs_out) EMEI_CHECK_ALIGN16(obs_out);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+#ifdef EMEI_HAVE_CARTPOLE_F32
+  if constexpr (sizeof(R) == 4) {  // lean float32 kernel (cartpole_f32.cuh)
+    cartpole_step_f32_dispatch(state_in, state_out, obs_out, action, reward, done, stats, n, *p, s);
+    return launch_status();
+  }
+#endif
   const CartPoleConsts<R> k = make_cartpole_consts<R>(*p);
   const int grid = grid_for(n, kBlock);
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (p->variant <= EMEI_CARTPOLE_SWINGUP)
     cartpole_step_kernel<R, false><<<grid, kBlock, 0, s>>>(state_in, state_out, obs_out, action, reward, done, stats, n, k);
   else

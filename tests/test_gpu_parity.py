@@ -140,7 +140,11 @@ def test_cartpole_teacher_forced_f32_trajectory(golden):
         env.state = prev
         obs = env.step(acts[:, t])[0].cpu().numpy()
         ref = traj[:, t, :4]
-        worst = max(worst, (np.abs(obs - ref) / (1e-6 + 1e-5 * np.abs(ref))).max())
+        # the un-reset reference trajectory winds theta up to hundreds of radians; casting that theta
+        # to float32 (the engine dtype) is an INPUT error of ulp32(theta)/2 that the step propagates
+        # (same allowance as test_cartpole_step_f32_vs_golden)
+        quant = np.spacing(np.abs(prev[:, 2]).astype(np.float32)).astype(np.float64)[:, None] * 40.0 * 0.02 * 4
+        worst = max(worst, (np.abs(obs - ref) / (1e-6 + 1e-5 * np.abs(ref) + quant)).max())
         prev = ref
     assert worst <= 1.0, f"worst envelope fraction {worst}"
 
@@ -382,7 +386,11 @@ def test_charged_ball_f32_teacher_forced(golden, tag):
     # landing re-derives (theta, omega) from asin near |arg| = 1 where float32 loses half its digits:
     # compare positions/velocities everywhere, and a looser bound on rows that just landed
     landed = r_on & ~on0
-    ok = within32(st["free_state"].cpu().numpy(), r_fr, 4.0).all(axis=1)
+    # on-circle rows rebuild (x, y, vx, vy) from sin/cos(theta): the float32 spacing of theta (input
+    # quantisation, |theta| reaches tens of radians) times (1 + |omega|) bounds what float32 can hold
+    quant = (np.spacing(np.abs(r_ci[:, 0]).astype(np.float32)).astype(np.float64) * (1.0 + np.abs(r_ci[:, 1])))[:, None]
+    got_fr = st["free_state"].cpu().numpy().astype(np.float64)
+    ok = (np.abs(got_fr - r_fr) <= 4.0 * (1e-6 + 1e-5 * np.abs(r_fr)) + quant * on0[:, None]).all(axis=1)
     assert ok[agree & ~landed].all()
     okc = within32(st["circle_state"].cpu().numpy(), r_ci, 4.0).all(axis=1)
     assert okc[agree & on0 & r_on].all()
