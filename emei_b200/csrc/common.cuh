@@ -25,6 +25,34 @@ inline int grid_for(int64_t n, int per_block) {
   return static_cast<int>(g);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Programmatic dependent launch (sm_90+): a rollout is a chain of short (~10 us) step kernels on one
+// stream, so the launch latency between them is a visible fraction of the step.  Kernels launched
+// through launch_pdl() may start (CTA scheduling, parameter loads, index arithmetic) while the tail
+// of the previous kernel in the stream drains; they call pdl_wait() before their first global
+// memory access, which blocks until the previous grid has fully completed and its writes are
+// visible, and pdl_trigger() at their top so that THEIR successor may be staged early in turn.
+// With a non-participating neighbour (memcpy, a torch kernel) both calls are no-ops and ordering is
+// the ordinary stream order.  Captured into CUDA graphs as programmatic edges.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), int grid, int block, cudaStream_t stream, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(static_cast<unsigned>(grid), 1, 1);
+  cfg.blockDim = dim3(static_cast<unsigned>(block), 1, 1);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // persistent launch: enough CTAs to cover n once, capped at ctas_per_sm resident CTAs on every SM
 // (the kernels grid-stride over the rest, so every SM carries the same number of units +-1)
 inline int persistent_grid(int64_t n, int per_block, int ctas_per_sm) {

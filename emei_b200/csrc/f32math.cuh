@@ -8,7 +8,7 @@
 //     (the classic single-precision kernels), quadrant fix-up with integer ops; |x| > 1e5 or
 //     non-finite x falls back to sincosf (Payne-Hanek) on a cold branch.
 //   * divisions by constants become multiplications by the double-rounded reciprocal; the one
-//     data-dependent division uses MUFU.RCP + one Newton step (<= 1 ulp).
+//     data-dependent division is one MUFU.RCP (<= 1 ulp) and a multiply.
 // Everything is __host__ __device__ so the numerics study runs the identical arithmetic on the CPU
 // (fmaf is exact on both sides; only MUFU.RCP is replaced by 1.0f/x on the host).
 #pragma once
@@ -20,6 +20,9 @@
 namespace emei {
 namespace f32 {
 
+#ifndef EMEI_F32_STUDY_RCP_ULP
+#define EMEI_F32_STUDY_RCP_ULP 0
+#endif
 #if defined(__CUDA_ARCH__)
 #define EMEI_F32_DEVICE 1
 #else
@@ -45,16 +48,19 @@ __host__ __device__ __forceinline__ float u2f(uint32_t u) {
 #endif
 }
 
-// 1/x for normal x of moderate magnitude: MUFU.RCP (<= 1 ulp) + one Newton step.
-__host__ __device__ __forceinline__ float rcp_nr(float x) {
+// 1/x for normal x of moderate magnitude: one MUFU.RCP (documented max error 1 ulp).  A Newton
+// step would halve that error; it is not worth 2 of the ~40 instructions of a sub-step (the
+// float32 rounding of the state dominates the per-step error budget: tools/f32_study).
+__host__ __device__ __forceinline__ float rcp_fast(float x) {
 #if EMEI_F32_DEVICE
   float r;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
 #else
-  float r = 1.0f / x;
+  // host study: worst case of the device instruction = the correctly rounded reciprocal off by 1 ulp
+  const float r = 1.0f / x;
+  return EMEI_F32_STUDY_RCP_ULP == 0 ? r : u2f(f2u(r) + EMEI_F32_STUDY_RCP_ULP);
 #endif
-  const float e = fmaf(-x, r, 1.0f);
-  return fmaf(r, e, r);
 }
 
 constexpr float kTwoOverPi = 0.636619772367581343f;
@@ -167,7 +173,7 @@ __host__ __device__ __forceinline__ void cartpole_substep(float& x, float& xd, f
   const float temp = fmaf(k.kpm * (w * w), s, f_mt);
   const float num = fmaf(k.g, s, -(c * temp));
   const float den = fmaf(-k.den1, c * c, k.den0);
-  const float th_acc = num * rcp_nr(den);
+  const float th_acc = num * rcp_fast(den);
   const float x_acc = fmaf(-k.kpm, th_acc * c, temp);
   x = fmaf(xd, k.dt, x);
   xd = fmaf(x_acc, k.dt, xd);

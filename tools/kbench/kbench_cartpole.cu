@@ -1,0 +1,157 @@
+// Kernel-level experiment harness (development tool, not shipped): times variants of the float32
+// cart-pole step kernel and a pure streaming kernel with the same 41 B/env traffic, on a ring of
+// batches larger than L2, K launches captured in one CUDA graph (same protocol as bench.py).
+//   nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -o /tmp/kbench tools/kbench/kbench_cartpole.cu
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+#include "../../emei_b200/csrc/cartpole_f32.cuh"
+
+using namespace emei;
+
+#define CK(x) do { cudaError_t err_ = (x); if (err_ != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(err_), __FILE__, __LINE__); exit(1);} } while (0)
+
+// pure streaming: same loads/stores, no math (the memory-system floor for this access pattern)
+template <int MINB>
+__global__ void __launch_bounds__(kBlock, MINB)
+stream_kernel(const float4* in, float4* out, const float* __restrict__ act, float* __restrict__ rew, uint8_t* __restrict__ done, uint32_t n) {
+  const uint32_t stride = gridDim.x * kBlock;
+  pdl_trigger();
+  pdl_wait();
+  for (uint32_t i = blockIdx.x * kBlock + threadIdx.x; i < n; i += stride) {
+    float4 y = in[i];
+    float a = __ldg(act + i);
+    y.x += a;
+    out[i] = y;
+    rew[i] = y.y;
+    done[i] = y.z > 0.f;
+  }
+}
+
+// compute only: the same per-env arithmetic on register-resident synthetic states, no HBM traffic
+template <int MINB, int FR>
+__global__ void __launch_bounds__(kBlock, MINB)
+compute_kernel(float* out, uint32_t n, const CartPoleF32Consts k) {
+  const uint32_t stride = gridDim.x * kBlock;
+  float acc = 0.f;
+  for (uint32_t i = blockIdx.x * kBlock + threadIdx.x; i < n; i += stride) {
+    float4 y = make_float4(1e-6f * i, 0.5f, 2e-6f * i, -1.0f);
+    const float f_mt = 1e-7f * i;
+    const float th_max = integrate<false, FR, false>(y, f_mt, 1.0f, k);
+    const float rew = fmaf(f32::cos_core(y.z), 0.5f, 0.5f);
+    acc += rew + y.x + y.y + y.w + th_max;
+  }
+  if (acc == 12345.678f) out[0] = acc;
+}
+
+struct Ring {
+  std::vector<float*> in, out, act, rew; std::vector<uint8_t*> done;
+};
+
+template <typename F>
+float time_graph(F launch, int K, cudaStream_t s, int reps = 5) {
+  if (getenv("KBENCH_NOGRAPH")) {  // plain stream launches (what ncu can see)
+    for (int i = 0; i < 3; ++i) launch(i);
+    CK(cudaStreamSynchronize(s));
+    return 0.f;
+  }
+  cudaGraph_t g; cudaGraphExec_t ge;
+  CK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+  for (int i = 0; i < K; ++i) launch(i);
+  CK(cudaStreamEndCapture(s, &g));
+  CK(cudaGraphInstantiate(&ge, g, 0));
+  CK(cudaGraphLaunch(ge, s)); CK(cudaStreamSynchronize(s));
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  float best = 1e30f;
+  for (int r = 0; r < reps; ++r) {
+    CK(cudaEventRecord(e0, s)); CK(cudaGraphLaunch(ge, s)); CK(cudaEventRecord(e1, s)); CK(cudaStreamSynchronize(s));
+    float ms; cudaEventElapsedTime(&ms, e0, e1); if (ms < best) best = ms;
+  }
+  cudaGraphExecDestroy(ge); cudaGraphDestroy(g);
+  return best * 1e3f / K;  // us per launch
+}
+
+template <int MINB, int FR, bool PDL, int S = 4, int DBG = 0>
+void run_cartpole(const char* name, Ring& R, uint32_t n, int K, cudaStream_t s, int grid_override = 0) {
+  emei_cartpole_params p = {};
+  p.gravity = 9.8; p.mass_pole = 0.1; p.total_mass = 1.1; p.length = 0.5; p.pole_mass_length = 0.05; p.force_mag = 10.0;
+  p.x_threshold = 5.0; p.theta_threshold = 0.2; p.dt = 0.02; p.freq_rate = 4; p.variant = EMEI_CARTPOLE_SWINGUP;
+  p.action_kind = EMEI_ACTION_CONTINUOUS_F32;
+  CartPoleF32Consts k = make_cartpole_f32_consts(p);
+  int grid = grid_override ? grid_override : persistent_grid(n, kBlock, MINB);
+  double* stats; CK(cudaMalloc(&stats, 16)); CK(cudaMemset(stats, 0, 16));
+  const int ring = (int)R.in.size();
+  auto launch = [&](int i) {
+    int j = i % ring;
+    auto kern = cartpole_step_f32_kernel<false, EMEI_ACTION_CONTINUOUS_F32, FR, MINB, false, S, DBG>;
+    if (PDL) launch_pdl(kern, grid, kBlock, s, (const float4*)R.in[j], (float4*)R.out[j], (float4*)nullptr, (const void*)R.act[j], R.rew[j], R.done[j], stats, n, k);
+    else kern<<<grid, kBlock, 0, s>>>((const float4*)R.in[j], (float4*)R.out[j], nullptr, R.act[j], R.rew[j], R.done[j], stats, n, k);
+  };
+  float us = time_graph(launch, K, s);
+  CK(cudaGetLastError());
+  printf("%-44s grid=%5d  %7.2f us/launch  %6.1f Genv-steps/s  %6.0f GB/s (41 B/env)\n", name, grid, us, n / us * 1e-3, 41.0 * n / us * 1e-3);
+  cudaFree(stats);
+}
+
+template <int MINB, int FR>
+void run_compute(const char* name, Ring& R, uint32_t n, int K, cudaStream_t s) {
+  emei_cartpole_params p = {};
+  p.gravity = 9.8; p.mass_pole = 0.1; p.total_mass = 1.1; p.length = 0.5; p.pole_mass_length = 0.05; p.force_mag = 10.0;
+  p.x_threshold = 5.0; p.theta_threshold = 0.2; p.dt = 0.02; p.freq_rate = 4; p.variant = EMEI_CARTPOLE_SWINGUP;
+  CartPoleF32Consts k = make_cartpole_f32_consts(p);
+  int grid = persistent_grid(n, kBlock, MINB);
+  auto launch = [&](int i) { compute_kernel<MINB, FR><<<grid, kBlock, 0, s>>>(R.rew[0], n, k); };
+  float us = time_graph(launch, K, s);
+  CK(cudaGetLastError());
+  printf("%-44s grid=%5d  %7.2f us/launch\n", name, grid, us);
+}
+
+template <int MINB, bool PDL>
+void run_stream(const char* name, Ring& R, uint32_t n, int K, cudaStream_t s) {
+  int grid = persistent_grid(n, kBlock, MINB);
+  const int ring = (int)R.in.size();
+  auto launch = [&](int i) {
+    int j = i % ring;
+    if (PDL) launch_pdl(stream_kernel<MINB>, grid, kBlock, s, (const float4*)R.in[j], (float4*)R.out[j], (const float*)R.act[j], R.rew[j], R.done[j], n);
+    else stream_kernel<MINB><<<grid, kBlock, 0, s>>>((const float4*)R.in[j], (float4*)R.out[j], R.act[j], R.rew[j], R.done[j], n);
+  };
+  float us = time_graph(launch, K, s);
+  CK(cudaGetLastError());
+  printf("%-44s grid=%5d  %7.2f us/launch  %6.1f Genv-steps/s  %6.0f GB/s (41 B/env)\n", name, grid, us, n / us * 1e-3, 41.0 * n / us * 1e-3);
+}
+
+int main(int argc, char** argv) {
+  const uint32_t n = argc > 1 ? (uint32_t)atol(argv[1]) : (1u << 20);
+  const int ring = argc > 2 ? atoi(argv[2]) : 8;
+  const int K = argc > 3 ? atoi(argv[3]) : 400;
+  cudaStream_t s; CK(cudaStreamCreate(&s));
+  Ring R;
+  std::vector<float> h(4 * (size_t)n), ha(n);
+  srand(1);
+  const float sc[4] = {4.f, 5.f, 3.14159f, 8.f};
+  for (size_t i = 0; i < 4 * (size_t)n; ++i) h[i] = (2.f * rand() / RAND_MAX - 1.f) * sc[i & 3];
+  for (size_t i = 0; i < n; ++i) ha[i] = 2.f * rand() / RAND_MAX - 1.f;
+  for (int j = 0; j < ring; ++j) {
+    float *a, *b, *c, *d; uint8_t* e;
+    CK(cudaMalloc(&a, 16 * (size_t)n)); CK(cudaMalloc(&b, 16 * (size_t)n)); CK(cudaMalloc(&c, 4 * (size_t)n)); CK(cudaMalloc(&d, 4 * (size_t)n)); CK(cudaMalloc(&e, n));
+    CK(cudaMemcpy(a, h.data(), 16 * (size_t)n, cudaMemcpyHostToDevice)); CK(cudaMemcpy(c, ha.data(), 4 * (size_t)n, cudaMemcpyHostToDevice));
+    R.in.push_back(a); R.out.push_back(b); R.act.push_back(c); R.rew.push_back(d); R.done.push_back(e);
+  }
+  printf("n=%u ring=%d K=%d\n", n, ring, K);
+  run_stream<8, false>("stream minb8", R, n, K, s);
+  run_stream<8, true>("stream minb8 pdl", R, n, K, s);
+  run_stream<6, true>("stream minb6 pdl", R, n, K, s);
+  run_compute<6, 4>("compute-only fr4 minb6", R, n, K, s);
+  run_compute<8, 4>("compute-only fr4 minb8", R, n, K, s);
+  run_compute<4, 4>("compute-only fr4 minb4", R, n, K, s);
+  run_compute<6, 0>("compute-only fr-runtime minb6", R, n, K, s);
+  run_cartpole<4, 0, true>("cartpole fr-runtime minb4 pdl", R, n, K, s);
+  run_cartpole<5, 0, true>("cartpole fr-runtime minb5 pdl", R, n, K, s);
+  run_cartpole<8, 0, true>("cartpole fr-runtime minb8 pdl", R, n, K, s);
+  run_cartpole<4, 4, true, 4>("cartpole fr4 minb4 S4", R, n, K, s);
+  run_cartpole<4, 4, true, 4, 1>("cartpole fr4 minb4 S4 NO-STORE", R, n, K, s);
+  run_cartpole<4, 4, true, 4, 2>("cartpole fr4 minb4 S4 NO-LOAD", R, n, K, s);
+  run_cartpole<6, 4, true, 4, 1>("cartpole fr4 minb6 S4 NO-STORE", R, n, K, s);
+  run_cartpole<6, 4, true, 4, 2>("cartpole fr4 minb6 S4 NO-LOAD", R, n, K, s);
+  return 0;
+}
