@@ -1,13 +1,21 @@
 #!/usr/bin/env python
-"""bench.py -- headline benchmark of the emei_b200 hot path (contract: see the task statement).
+"""bench.py -- benchmark of the emei_b200 hot path (contract: see the task statement / DESIGN.md 6).
 
-Workload (BASELINE.json configs[1], "C2"): ContinuousCartPoleSwingUp batched step, 2^20 envs per
-GPU, freq_rate=4 forward-Euler sub-steps, float32.  A "step" is one launch of the step kernel over
-one 2^20-env batch.  Batches rotate over a ring whose footprint exceeds L2 (config.l2_policy), so
-every timed launch streams its state from HBM.
+Default workload = BASELINE.json configs[1] ("c2"): ContinuousCartPoleSwingUp batched step, 2^20 envs
+per GPU, freq_rate=4 forward-Euler sub-steps, float32.  A "step" is one pass of the hot path over
+one batch.  The other BASELINE configs are selectable with --workload (they are parity-test sizes
+and secondary bench lines, committed under profiles/):
 
-  python bench.py [--gpus N --steps K --warmup W]            # our arm (torchrun for N>1)
-  python bench.py --impl reference [--steps K --warmup W]    # CPU arm: the oracle port on host cores
+  c1            BoundaryInvertedPendulumSwingUp step, 4096 envs, freq_rate=1   (launch-latency bound)
+  c2 (default)  ContinuousCartPoleSwingUp step, 2^20 envs/GPU, freq_rate=4
+  c3_hopper     Hopper get_batch_reward+get_batch_terminal, 2^24 transitions/GPU (terminate_when_unhealthy=False)
+  c3_halfcheetah  HalfCheetah same, 2^24 transitions/GPU
+  c4            ChargedBallCentering step, 2^26 envs TOTAL sharded over the ranks (strong scaling)
+  c5            scoring 2^26 transitions/GPU (half Hopper, half HalfCheetah) + freeze/unfreeze of a
+                2^26-env cart-pole state buffer per sweep
+
+  python bench.py [--gpus N --steps K --warmup W] [--workload W]          # our arm (torchrun for N>1)
+  python bench.py --impl reference [--steps K --warmup W] [--workload W]  # CPU arm: the oracle port on host cores
 
 One JSON line on stdout (rank 0).
 """
@@ -24,61 +32,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-N_ENVS = 1 << 20
-FREQ_RATE = 4
 DT = 0.02
-ALG_BYTES_PER_ENV_STEP = 41  # state 16 + action 4 + next 16 + reward 4 + done 1
-METRIC = "env_steps_per_sec"
-UNIT = "env-steps/s"
-WORKLOAD = "ContinuousCartPoleSwingUp batched step, 2^20 envs/GPU, freq_rate=4, float32 (BASELINE configs[1])"
-
-
-def synth_inputs(n, seed=1002):
-    """[x, x', th, th'] = U(-1,1)*[4,5,pi,8] (+1% slice with |x| at the terminal
-    threshold), action U(-1,1) float32 [n,1]."""
-    rng = np.random.default_rng(seed)
-    st = (rng.uniform(-1, 1, size=(n, 4)) * np.array([4.0, 5.0, np.pi, 8.0])).astype(np.float32)
-    k = n // 100
-    st[:k, 0] = np.sign(st[:k, 0]) * rng.uniform(4.99, 5.01, size=k).astype(np.float32)
-    act = rng.uniform(-1, 1, size=(n, 1)).astype(np.float32)
-    return st, act
-
-
-# --------------------------------------------------------------------------------------------------
-# CPU arm: the oracle port (numpy restatement of the reference's step) on the host cores
-# --------------------------------------------------------------------------------------------------
-def _cpu_worker(args):
-    st, act, reps = args
-    from oracle import emei_oracle as O
-
-    p = O.cartpole_params("continuous_swingup")
-    t0 = time.perf_counter()
-    for _ in range(reps):
-        force = O.cartpole_force(act, True, p)
-        nxt = O.cartpole_step_f64ref(st, force, DT, FREQ_RATE, p, libm=False)
-        O.cartpole_reward("continuous_swingup", nxt)
-        O.cartpole_terminal("continuous_swingup", nxt, p)
-    return time.perf_counter() - t0
-
-
-def cpu_step_rate(sample_envs, steps, cores):
-    """env-steps/s of the oracle port: `cores` processes, each stepping sample_envs/cores envs."""
-    import multiprocessing as mp
-
-    st, act = synth_inputs(sample_envs)
-    st = st.astype(np.float64)
-    chunks = [(st[i::cores].copy(), act[i::cores].copy(), steps) for i in range(cores)]
-    if cores == 1:
-        t0 = time.perf_counter()
-        _cpu_worker(chunks[0])
-        wall = time.perf_counter() - t0
-    else:
-        with mp.get_context("fork").Pool(cores) as pool:
-            pool.map(_cpu_worker, [(c[0][:1024], c[1][:1024], 1) for c in chunks])  # spin the workers up
-            t0 = time.perf_counter()
-            pool.map(_cpu_worker, chunks)
-            wall = time.perf_counter() - t0
-    return sample_envs * steps / wall, wall
 
 
 def host_cores():
@@ -88,46 +42,427 @@ def host_cores():
         return os.cpu_count() or 1
 
 
+# ==================================================================================================
+# synthetic inputs: generated on the host, seeded, identical bits for CPU and GPU arms
+# ==================================================================================================
+def synth_cartpole(n, seed=1002):
+    """C2: [x, x', th, th'] = U(-1,1)*[4,5,pi,8] (+1% slice with |x| at the terminal threshold), action U(-1,1)."""
+    rng = np.random.default_rng(seed)
+    st = (rng.uniform(-1, 1, size=(n, 4)) * np.array([4.0, 5.0, np.pi, 8.0])).astype(np.float32)
+    k = n // 100
+    st[:k, 0] = np.sign(st[:k, 0]) * rng.uniform(4.99, 5.01, size=k).astype(np.float32)
+    act = rng.uniform(-1, 1, size=(n, 1)).astype(np.float32)
+    return st, act
+
+
+def synth_ip(n, seed=1001):
+    """C1: [x, th, v, w] = U(-1,1)*[1.9, pi, 5, 8], ctrl U(-3,3)."""
+    rng = np.random.default_rng(seed)
+    st = (rng.uniform(-1, 1, size=(n, 4)) * np.array([1.9, np.pi, 5.0, 8.0])).astype(np.float32)
+    act = rng.uniform(-3, 3, size=(n, 1)).astype(np.float32)
+    return st, act
+
+
+def synth_scoring(n, family, seed=1003):
+    """C3: Hopper obs = [0,1.25,0..] + N(0,1)*[1,.4,.15,1..]; HalfCheetah obs N(0,1)[n,18]; pre_obs = obs with
+    column 0 shifted by N(0, 0.01); action U(-1,1); 0.1% rows poisoned with NaN/Inf."""
+    rng = np.random.default_rng(seed + (0 if family == "hopper" else 1))
+    d, da = (12, 3) if family == "hopper" else (18, 6)
+    obs = rng.standard_normal((n, d), dtype=np.float32)
+    if family == "hopper":
+        obs *= np.array([1, 0.4, 0.15] + [1] * 9, dtype=np.float32)
+        obs[:, 1] += 1.25
+    pre = obs.copy()
+    pre[:, 0] -= 0.01 * rng.standard_normal(n, dtype=np.float32)
+    act = rng.uniform(-1, 1, size=(n, da)).astype(np.float32)
+    bad = rng.integers(0, n, size=max(1, n // 1000))
+    obs[bad, rng.integers(0, d, size=bad.shape[0])] = rng.choice(np.array([np.nan, np.inf, -np.inf], dtype=np.float32), size=bad.shape[0])
+    return obs, pre, act
+
+
+# ==================================================================================================
+# CPU arm: the oracle port (numpy restatement of the reference) on the host cores.  bench.py's
+# cpu_baseline / --impl reference are the ONLY product-side users of oracle/ (as the thing timed
+# beside the GPU path, never inside it).
+# ==================================================================================================
+def _cpu_worker(args):
+    kind, arrays, reps = args
+    from oracle import emei_oracle as O
+
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        if kind == "c2":
+            st, act = arrays
+            p = O.cartpole_params("continuous_swingup")
+            nxt = O.cartpole_step_f64ref(st, O.cartpole_force(act, True, p), DT, 4, p, libm=False)
+            O.cartpole_reward("continuous_swingup", nxt)
+            O.cartpole_terminal("continuous_swingup", nxt, p)
+        elif kind == "c1":
+            st, act = arrays
+            p = O.InvertedPendulumParams()
+            nxt, obs = O.ip_step(st, act[:, 0].astype(np.float64), DT, 1, True, p)
+            O.ip_reward("ip_boundary_swingup", obs)
+            O.ip_terminal("ip_boundary_swingup", obs, p)
+        elif kind == "c3_hopper":
+            obs, pre, act = arrays
+            p = O.HopperParams(terminate_when_unhealthy=False)
+            O.hopper_reward(obs, pre, act, p)
+            O.hopper_terminal(obs, p)
+        elif kind == "c3_halfcheetah":
+            obs, pre, act = arrays
+            p = O.HalfCheetahParams()
+            O.halfcheetah_reward(obs, pre, act, p)
+            O.halfcheetah_terminal(obs)
+        elif kind == "c4":
+            on, ci, fr, act = arrays
+            p = O.ChargedBallParams()
+            on, ci, fr = O.charged_ball_step(on, ci, fr, O.charged_ball_force(act, False, p), 1, p)
+            O.charged_ball_reward(fr, p)
+        else:
+            raise ValueError(kind)
+    return time.perf_counter() - t0
+
+
+def _cpu_inputs(kind, n):
+    if kind == "c2":
+        st, act = synth_cartpole(n)
+        return [st.astype(np.float64), act]
+    if kind == "c1":
+        st, act = synth_ip(n)
+        return [st.astype(np.float64), act]
+    if kind in ("c3_hopper", "c3_halfcheetah"):
+        obs, pre, act = synth_scoring(n, kind[3:])
+        return [obs.astype(np.float64), pre.astype(np.float64), act.astype(np.float64)]
+    if kind == "c4":
+        from oracle import emei_oracle as O
+
+        rng = np.random.default_rng(1004)
+        on, ci, fr = O.charged_ball_init_state(n, rng, O.ChargedBallParams())
+        return [on, ci, fr, rng.integers(0, 2, size=n)]
+    raise ValueError(kind)
+
+
+def cpu_rate(kind, sample_units, reps, cores):
+    """units/s of the oracle port: `cores` processes, each owning sample_units/cores units."""
+    import multiprocessing as mp
+
+    arrays = _cpu_inputs(kind, sample_units)
+    chunks = [(kind, [a[i::cores].copy() for a in arrays], reps) for i in range(cores)]
+    with np.errstate(all="ignore"):
+        if cores == 1:
+            t0 = time.perf_counter()
+            _cpu_worker(chunks[0])
+            wall = time.perf_counter() - t0
+        else:
+            with mp.get_context("fork").Pool(cores) as pool:
+                pool.map(_cpu_worker, [(kind, [a[:256] for a in c[1]], 1) for c in chunks])  # spin the workers up
+                t0 = time.perf_counter()
+                pool.map(_cpu_worker, chunks)
+                wall = time.perf_counter() - t0
+    return sample_units * reps / wall, wall
+
+
+# ==================================================================================================
+# workloads
+# ==================================================================================================
+class Workload:
+    key = name = metric = unit = kernel = ""
+    dtype = "f32"
+    scaling = "weak"
+    use_graph = True
+    alg_bytes = 0  # algorithmic bytes per unit (SURVEY.md 8d / DESIGN.md 5)
+    cpu_kind = None  # which oracle routine is the CPU baseline
+    cpu_sample = 1 << 20
+
+    def __init__(self, args, rank, world, dev):
+        self.args, self.rank, self.world, self.dev = args, rank, world, dev
+
+    # units processed by THIS rank in one step
+    units = 0
+
+    def setup(self):
+        raise NotImplementedError
+
+    def step(self, i):
+        raise NotImplementedError
+
+    def setup_e2e(self):
+        raise NotImplementedError
+
+    def step_e2e(self, i):
+        raise NotImplementedError
+
+    def config(self):
+        return {}
+
+    def dominant_kernel_ms(self, ms_per_step):
+        """duration of the dominant kernel per launch; default: the whole step is that one kernel."""
+        return ms_per_step
+
+
+class CartPoleStep(Workload):
+    """C2 (and, with the IP env, C1): ring of independent batches larger than L2, rotated every launch."""
+
+    key, metric, unit = "c2", "env_steps_per_sec", "env-steps/s"
+    name = "ContinuousCartPoleSwingUp batched step, 2^20 envs/GPU, freq_rate=4, float32 (BASELINE configs[1])"
+    kernel = "emei::cartpole_step_f32_kernel<IP=0, AK=f32, FR=4>"
+    env_id, n_envs, freq_rate, ring = "ContinuousCartPoleSwingUp-v0", 1 << 20, 4, 8
+    alg_bytes = 41  # state 16 + action 4 + next 16 + reward 4 + done 1
+    cpu_kind = "c2"
+    inst_per_unit = 250.0  # warp-level SASS instructions per env-step, from ncu smsp__inst_executed (profiles/)
+
+    def synth(self, seed):
+        return synth_cartpole(self.n_envs, seed)
+
+    def setup(self):
+        import torch
+
+        import emei_b200 as E
+
+        self.units = self.n_envs
+        ring = self.args.ring or self.ring
+        st, act = self.synth(1002 + self.rank)
+        self.envs, self.acts = [], []
+        for j in range(ring):
+            env = E.make(self.env_id, freq_rate=self.freq_rate, real_time_scale=DT, num_envs=self.n_envs,
+                         dtype=torch.float32, device=self.dev, env_offset=(self.rank * ring + j) * self.n_envs)
+            env.state = np.roll(st, j * 4099, axis=0)
+            env._stats = self.envs[0].stats if self.envs else env.stats  # one shared statistics buffer
+            self.envs.append(env)
+            self.acts.append(torch.as_tensor(np.roll(act, j * 4099, axis=0)).to(self.dev).reshape(self.n_envs))
+        self.envs[0].reset_stats()
+        self.stats = self.envs[0].stats
+        self._act_host = act
+
+    def step(self, i):
+        j = i % len(self.envs)
+        self.envs[j].step(self.acts[j])
+
+    def setup_e2e(self):
+        import torch
+
+        a = self._act_host
+        self.act_host = [torch.as_tensor(np.roll(a, j * 4099, axis=0).reshape(self.n_envs)).pin_memory() for j in range(4)]
+        self.env0 = self.envs[0]
+        self.env0.step_host(self.act_host[0])
+        self.h2d, self.d2h = self.env0._staging.h2d_bytes, self.env0._staging.d2h_bytes
+        self.e2e_api = "env.step_host(action_host) -> numpy obs/reward/terminated (pinned staging, chunked copy/compute overlap)"
+
+    def step_e2e(self, i):
+        self.env0.step_host(self.act_host[i % len(self.act_host)])
+
+    def config(self):
+        ring = len(self.envs)
+        mb = ring * self.n_envs * self.alg_bytes / 1e6
+        return {
+            "envs_per_gpu": self.n_envs, "freq_rate": self.freq_rate, "real_time_scale": DT,
+            "l2_policy": f"inputs larger than L2: ring of {ring} independent {self.n_envs}-env batches ({mb:.0f} MB of step traffic) rotated every launch",
+        }
+
+
+class IPStep(CartPoleStep):
+    key = "c1"
+    name = "BoundaryInvertedPendulumSwingUp batched step, 4096 envs, freq_rate=1, float32 (BASELINE configs[0])"
+    kernel = "emei::cartpole_step_f32_kernel<IP=1, AK=f32, FR=1>"
+    env_id, n_envs, freq_rate, ring = "BoundaryInvertedPendulumSwingUp-v0", 4096, 1, 1024
+    alg_bytes = 57  # state 16 + action 4 + next state 16 + wrapped obs 16 + reward 4 + done 1
+    cpu_kind, cpu_sample = "c1", 1 << 20
+    inst_per_unit = 130.0
+
+    def synth(self, seed):
+        return synth_ip(self.n_envs, seed)
+
+
+class Scoring(Workload):
+    """C3: fused get_batch_reward + get_batch_terminal over n transitions resident in HBM (>> L2)."""
+
+    metric, unit = "transitions_per_sec", "transitions/s"
+    use_graph = False
+    family, n = "hopper", 1 << 24
+    env_kwargs = {}
+
+    def setup(self):
+        import torch
+
+        import emei_b200 as E
+
+        self.units = self.n
+        self.env = E.make(self.env_id, dtype=torch.float32, device=self.dev, **self.env_kwargs)
+        obs, pre, act = synth_scoring(self.n, self.family, 1003 + 17 * self.rank)
+        self._host = (obs, pre, act)
+        self.obs, self.pre, self.act = (torch.as_tensor(a).to(self.dev) for a in (obs, pre, act))
+        self.stats = self.env.stats
+        self._ev = []
+
+    def step(self, i):
+        self.out = self.env.get_batch_reward_terminal(self.obs, self.pre, self.act)
+
+    def setup_e2e(self):
+        import torch
+
+        self.h_in = [torch.as_tensor(a).pin_memory() for a in self._host]
+        self.h_r = torch.empty((self.n, 1), dtype=torch.float32).pin_memory()
+        self.h_d = torch.empty((self.n, 1), dtype=torch.bool).pin_memory()
+        self.h2d = sum(t.numel() * t.element_size() for t in self.h_in)
+        self.d2h = self.h_r.numel() * 4 + self.h_d.numel()
+        self.e2e_api = "env.get_batch_reward_terminal(obs, pre_obs, action) with pinned HOST tensors -> reward/terminal copied back to pinned host"
+
+    def step_e2e(self, i):
+        import torch
+
+        r, d = self.env.get_batch_reward_terminal(*self.h_in)
+        self.h_r.copy_(r, non_blocking=True)
+        self.h_d.copy_(d, non_blocking=True)
+        torch.cuda.current_stream(self.dev).synchronize()
+
+    def config(self):
+        return {"transitions_per_gpu": self.n, "l2_policy": f"inputs larger than L2 ({self.n * self.alg_bytes / 1e6:.0f} MB per sweep)",
+                "note": "step = emei_sumsq (batch-wide control cost, 1 launch) + fused emei_reward_terminal (1 launch)"}
+
+
+class HopperScoring(Scoring):
+    key, family, env_id = "c3_hopper", "hopper", "HopperRunning-v0"
+    name = "Hopper get_batch_reward+get_batch_terminal, 2^24 transitions/GPU, terminate_when_unhealthy=False, float32 (BASELINE configs[2])"
+    kernel = "emei::reward_terminal_kernel<float, HOPPER> (+ emei::sumsq_kernel<float>)"
+    env_kwargs = {"terminate_when_unhealthy": False}
+    alg_bytes = 69  # obs 48 + pre_obs[:,0] 4 + action 12 + reward 4 + done 1
+    cpu_kind, cpu_sample = "c3_hopper", 1 << 22
+
+
+class HalfCheetahScoring(Scoring):
+    key, family, env_id = "c3_halfcheetah", "halfcheetah", "HalfCheetahRunning-v0"
+    name = "HalfCheetah get_batch_reward+get_batch_terminal, 2^24 transitions/GPU, float32 (BASELINE configs[2])"
+    kernel = "emei::reward_terminal_kernel<float, HALFCHEETAH> (+ emei::sumsq_kernel<float>)"
+    alg_bytes = 105  # obs 72 + pre_obs[:,0] 4 + action 24 + reward 4 + done 1
+    cpu_kind, cpu_sample = "c3_halfcheetah", 1 << 22
+
+
+class ChargedBall(Workload):
+    """C4: 2^26 envs in total, sharded contiguously over the ranks (strong scaling); state updated in place."""
+
+    key, metric, unit = "c4", "env_steps_per_sec", "env-steps/s"
+    name = "ChargedBallCentering batched step, 2^26 envs total sharded over the ranks, freq_rate=1, float32 (BASELINE configs[3])"
+    kernel = "emei::charged_ball_step_kernel<float>"
+    scaling, use_graph = "strong", False
+    total = 1 << 26
+    alg_bytes = 56  # state in 25 + action 1 (uint8) + state out 25 + reward 4 + done 1
+    cpu_kind, cpu_sample = "c4", 1 << 20
+
+    def setup(self):
+        import torch
+
+        import emei_b200 as E
+        from emei_b200.dist import shard_range
+
+        b, e = shard_range(self.total, self.rank, self.world)
+        self.units = e - b
+        self.env = E.make("ChargedBallCentering-v0", num_envs=self.units, dtype=torch.float32, device=self.dev, env_offset=b)
+        self.env.reset(seed=1004)
+        g = torch.Generator(device=self.dev)
+        g.manual_seed(1004 + self.rank)
+        self.acts = [torch.randint(0, 2, (self.units,), device=self.dev, dtype=torch.uint8, generator=g) for _ in range(4)]
+        self.env.reset_stats()
+        self.stats = self.env.stats
+
+    def step(self, i):
+        self.env.step(self.acts[i % 4])
+
+    def setup_e2e(self):
+        import torch
+
+        self.act_host = [a.cpu().pin_memory() for a in self.acts]
+        self.env.step_host(self.act_host[0])
+        self.h2d, self.d2h = self.env._staging.h2d_bytes, self.env._staging.d2h_bytes
+        self.e2e_api = "env.step_host(action_host) -> numpy obs/reward/terminated (pinned staging)"
+
+    def step_e2e(self, i):
+        self.env.step_host(self.act_host[i % 4])
+
+    def config(self):
+        return {"envs_total": self.total, "envs_per_gpu": self.units, "freq_rate": 1,
+                "l2_policy": f"inputs larger than L2 ({self.units * self.alg_bytes / 1e6:.0f} MB per step per GPU)"}
+
+
+class ScoringSweep(Workload):
+    """C5: one imagined-rollout scoring sweep per step = freeze() of a 2^26-env cart-pole state buffer,
+    Hopper + HalfCheetah reward/terminal over 2^25 transitions each, unfreeze()."""
+
+    key, metric, unit = "c5", "transitions_per_sec", "transitions/s"
+    name = "MBRL scoring sweep: 2^26 transitions/GPU (half Hopper, half HalfCheetah) reward+terminal + freeze/unfreeze of a 2^26-env cart-pole buffer, float32 (BASELINE configs[4])"
+    kernel = "emei::reward_terminal_kernel<float, HALFCHEETAH> (dominant), HOPPER, sumsq, snapshot_copy"
+    use_graph = False
+    n_half, n_env = 1 << 25, 1 << 26
+    # per transition: (69 + 105)/2 scoring + 2 x (16 read + 16 write) snapshot bytes per env over n_env == 2*n_half transitions
+    alg_bytes = (69 + 105) / 2 + 64
+    cpu_kind, cpu_sample = "c3_hopper", 1 << 22
+
+    def setup(self):
+        import torch
+
+        import emei_b200 as E
+
+        self.units = 2 * self.n_half
+        self.hop = E.make("HopperRunning-v0", terminate_when_unhealthy=False, dtype=torch.float32, device=self.dev)
+        self.chee = E.make("HalfCheetahRunning-v0", dtype=torch.float32, device=self.dev)
+        self.cp = E.make("CartPoleSwingUp-v0", num_envs=self.n_env, dtype=torch.float32, device=self.dev)
+        self.cp.reset(seed=1005)
+        self.data = []
+        for fam in ("hopper", "halfcheetah"):
+            obs, pre, act = synth_scoring(self.n_half, fam, 1005 + 31 * self.rank)
+            self.data.append(tuple(torch.as_tensor(a).to(self.dev) for a in (obs, pre, act)))
+        self.stats = self.hop.stats
+
+    def step(self, i):
+        self.cp.freeze()
+        self.o1 = self.hop.get_batch_reward_terminal(*self.data[0])
+        self.o2 = self.chee.get_batch_reward_terminal(*self.data[1])
+        self.cp.unfreeze()
+
+    def setup_e2e(self):
+        self.h2d = self.d2h = 0
+        self.e2e_api = None
+
+    def config(self):
+        return {"transitions_per_gpu": self.units, "snapshot_envs_per_gpu": self.n_env,
+                "l2_policy": "inputs larger than L2 (10 GB per sweep)"}
+
+
+WORKLOADS = {w.key: w for w in (IPStep, CartPoleStep, HopperScoring, HalfCheetahScoring, ChargedBall, ScoringSweep)}
+
+
+# ==================================================================================================
+# reference arm
+# ==================================================================================================
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    W = WORKLOADS[args.workload]
     cores = host_cores()
-    # calibrate, then size the per-step sample so the whole run stays within ~2 minutes
-    rate1, _ = cpu_step_rate(1 << 16, 1, 1)
-    budget_s = 100.0
+    kind = W.cpu_kind
+    rate1, _ = cpu_rate(kind, 1 << 14, 1, 1)  # calibrate, then size the per-step sample for ~100 s in total
     total_steps = args.steps + args.warmup
-    sample = int(min(N_ENVS, max(1 << 12, rate1 * cores * 0.6 * budget_s / total_steps)))
+    sample = int(min(W.cpu_sample * 4, max(1 << 12, rate1 * cores * 0.6 * 100.0 / total_steps)))
     sample -= sample % cores
     if args.warmup:
-        cpu_step_rate(sample, args.warmup, cores)
-    rate, wall = cpu_step_rate(sample, args.steps, cores)
-    desc = f"{sample} envs/step x {args.steps} steps of the numpy oracle port (oracle/emei_oracle.py), {cores} processes"
+        cpu_rate(kind, sample, args.warmup, cores)
+    rate, wall = cpu_rate(kind, sample, args.steps, cores)
+    desc = f"{sample} units/step x {args.steps} steps of the numpy oracle port (oracle/emei_oracle.py, kind={kind}), {cores} processes"
     line = {
-        "impl": "reference",
-        "metric": METRIC,
-        "value": rate,
-        "unit": UNIT,
-        "n_gpus": args.gpus,
-        "steps": args.steps,
-        "warmup": args.warmup,
-        "ms_per_step": 1e3 * wall / args.steps,
-        "higher_is_better": True,
-        "scaling": "weak",
-        "vs_baseline": None,
-        "dtype": "f64",
-        "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample_envs_per_step": sample},
-        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
-        "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "impl": "reference", "metric": W.metric, "value": rate, "unit": W.unit, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps, "higher_is_better": True, "scaling": W.scaling,
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": W.name, "sample_units_per_step": sample},
+        "cpu_baseline": {"value": rate, "unit": W.unit, "cores": cores, "kind": "port", "sample": desc},
+        "e2e": {"value": rate, "unit": W.unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
 
 
-# --------------------------------------------------------------------------------------------------
+# ==================================================================================================
 # GPU arm
-# --------------------------------------------------------------------------------------------------
+# ==================================================================================================
 class ClockSampler(threading.Thread):
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
 
@@ -141,7 +476,7 @@ class ClockSampler(threading.Thread):
     def run(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True,
             )
             for ln in self.proc.stdout:
@@ -168,21 +503,21 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def measured_hbm_peak():
+def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
         try:
-            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+            d = json.load(open(path))
+            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)", float(d.get("sm_max_mhz", 1965.0))
         except Exception:
             pass
-    return 6650.0, "fallback (B200_PROFILING.md)"
+    return 6650.0, "fallback (B200_PROFILING.md)", 1965.0
 
 
 def run_ours(args):
     import torch
     import torch.distributed as dist
 
-    import emei_b200 as E
     from emei_b200 import _lib
 
     rank = int(os.environ.get("RANK", "0"))
@@ -194,149 +529,137 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    K, W = args.steps, args.warmup
-    ring = args.ring
-    st, act = synth_inputs(N_ENVS, seed=1002 + rank)
-    # ring of independent 2^20-env batches: 41 MB of step traffic each, ring*41 MB >> 126 MB of L2
-    envs, acts = [], []
-    for j in range(ring):
-        env = E.make("ContinuousCartPoleSwingUp-v0", freq_rate=FREQ_RATE, real_time_scale=DT, num_envs=N_ENVS,
-                     dtype=torch.float32, device=dev, env_offset=(rank * ring + j) * N_ENVS)
-        env.state = np.roll(st, j * 4099, axis=0)
-        env._stats = envs[0].stats if envs else env.stats  # one shared statistics buffer
-        envs.append(env)
-        acts.append(torch.as_tensor(np.roll(act, j * 4099, axis=0)).to(dev).reshape(N_ENVS))
-    envs[0].reset_stats()
+    K, W = args.steps, max(args.warmup, 3)
+    wl = WORKLOADS[args.workload](args, rank, world, dev)
+    wl.setup()
 
-    def one_step(i):
-        envs[i % ring].step(acts[i % ring])
-
-    # ---------------- device-resident value: W warm-up steps, then EXACTLY K steps in one CUDA graph
-    for i in range(max(W, 3)):
-        one_step(i)
+    for i in range(W):
+        wl.step(i)
     torch.cuda.synchronize()
     launches0 = _lib.launch_count
-    graph = torch.cuda.CUDAGraph()
-    side = torch.cuda.Stream(dev)
-    with torch.cuda.stream(side):
-        with torch.cuda.graph(graph, stream=side):
-            for i in range(K):
-                one_step(i)
-    launches_per_replay = _lib.launch_count - launches0
+    graph = None
+    if wl.use_graph:  # launch-bound steps: K launches captured once, replayed as one graph
+        graph = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream(dev)
+        with torch.cuda.stream(side):
+            with torch.cuda.graph(graph, stream=side):
+                for i in range(K):
+                    wl.step(i)
+        launches = _lib.launch_count - launches0
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
         time.sleep(0.3)
-    graph.replay()  # warm the instantiated graph (also puts the GPU under load for the clock samples)
+    if graph is not None:
+        graph.replay()  # warm the instantiated graph (also puts the GPU under load for the clock samples)
+    else:
+        wl.step(0)
     torch.cuda.synchronize()
-    stats_buf = envs[0].stats
-    envs[0].reset_stats()
+    _lib.call("emei_stats_reset", wl.stats.data_ptr(), torch.cuda.current_stream(dev).cuda_stream, launches=0)
+    launches0 = _lib.launch_count
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    reps = 1  # EXACTLY K steps are timed
     ev0.record()
-    for _ in range(reps):
+    if graph is not None:
         graph.replay()
+    else:
+        for i in range(K):
+            wl.step(i)
     ev1.record()
     if world > 1:
-        dist.all_reduce(stats_buf)  # end-of-rollout statistics: 2 doubles over NCCL/NVLink
+        dist.all_reduce(wl.stats)  # end-of-rollout statistics: 2 doubles over NCCL/NVLink
     torch.cuda.synchronize()
+    if graph is None:
+        launches = _lib.launch_count - launches0
     if world > 1:
         dist.barrier()
-    ms_total = ev0.elapsed_time(ev1) / reps
-    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+    units = torch.tensor([float(wl.units)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(units)
     ms_total = float(t.item())
     ms_per_step = ms_total / K
-    value = world * N_ENVS * K / (ms_total * 1e-3)
+    value = float(units.item()) * K / (ms_total * 1e-3)
 
-    # ---------------- e2e: host actions in, host obs/reward/done out, every step (public step_host API)
-    e2e_steps = max(3, min(K, args.e2e_steps))
-    act_host = [torch.as_tensor(np.roll(act, j * 4099, axis=0).reshape(N_ENVS)).pin_memory() for j in range(min(ring, 4))]
-    env0 = envs[0]
-    for i in range(3):
-        env0.step_host(act_host[i % len(act_host)])
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    t0 = time.perf_counter()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(e2e_steps):
-        env0.step_host(act_host[i % len(act_host)])
-    e1.record()
-    torch.cuda.synchronize()
-    e2e_ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3)
-    te = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = world * N_ENVS * e2e_steps / (float(te.item()) * 1e-3)
+    # ---------------- dominant-kernel duration for the roofline (CUDA events around that kernel alone)
+    kern_ms = ms_per_step
+    if not wl.use_graph and hasattr(wl, "env") and args.workload.startswith("c3"):
+        from emei_b200 import engine
+
+        kern_ms = engine.time_fused_scoring(wl.env, wl.obs, wl.pre, wl.act, reps=max(3, min(K, 10)))
+
+    # ---------------- e2e: host inputs in, host results out, every step, through the public API
+    e2e = None
+    wl.setup_e2e()
+    if wl.e2e_api is not None:
+        e2e_steps = max(3, min(K, args.e2e_steps))
+        for i in range(2):
+            wl.step_e2e(i)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(e2e_steps):
+            wl.step_e2e(i)
+        e1.record()
+        torch.cuda.synchronize()
+        e2e_ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3)
+        te = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e = {
+            "value": float(units.item()) * e2e_steps / (float(te.item()) * 1e-3), "unit": wl.unit,
+            "h2d_bytes_per_step": wl.h2d, "d2h_bytes_per_step": wl.d2h, "steps": e2e_steps, "api": wl.e2e_api,
+        }
     clocks = sampler.finish() if rank == 0 else None
-
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    peak, peak_src = measured_hbm_peak()
-    achieved = ALG_BYTES_PER_ENV_STEP * N_ENVS / (ms_per_step * 1e-3) / 1e9
-    line = {
-        "metric": METRIC,
-        "value": value,
-        "unit": UNIT,
-        "n_gpus": world,
-        "steps": K,
-        "warmup": max(W, 3),
-        "ms_per_step": ms_per_step,
-        "higher_is_better": True,
-        "scaling": "weak",
-        "vs_baseline": None,
-        "dtype": "f32",
-        "data": "synthetic",
-        "config": {
-            "workload": WORKLOAD,
-            "envs_per_gpu": N_ENVS,
-            "freq_rate": FREQ_RATE,
-            "real_time_scale": DT,
-            "l2_policy": f"inputs larger than L2: ring of {ring} independent 2^20-env batches ({ring * 41} MB of step traffic) rotated every launch",
-            "launch": f"K={K} step launches captured in one CUDA graph, replayed once; CUDA events on the launching stream",
-            "parallelism": f"env batch sharded, {world} rank(s), no data-path collective",
-        },
-        "roofline": {
-            "bound": "hbm",
-            "achieved": achieved,
-            "peak": peak,
-            "unit": "GB/s",
-            "frac": achieved / peak,
-            "traffic": None,
-            "peak_source": peak_src,
-            "algorithmic_bytes_per_env_step": ALG_BYTES_PER_ENV_STEP,
-            "kernel": "emei::cartpole_step_kernel<float,false>",
-            "note": "duration = timed region / launches (includes inter-launch gaps)",
-        },
-        "e2e": {
-            "value": e2e_value,
-            "unit": UNIT,
-            "h2d_bytes_per_step": env0._staging.h2d_bytes,
-            "d2h_bytes_per_step": env0._staging.d2h_bytes,
-            "steps": e2e_steps,
-            "api": "env.step_host(action_host) -> numpy obs/reward/terminated (pinned staging, sync per step)",
-        },
-        "gpu_launches": launches_per_replay * reps,
-        "clocks": clocks,
+    peak, peak_src, sm_mhz = measured_peaks()
+    achieved = wl.alg_bytes * wl.units / (kern_ms * 1e-3) / 1e9
+    roofline = {
+        "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+        "peak_source": peak_src, "algorithmic_bytes_per_unit": wl.alg_bytes, "kernel": wl.kernel,
+        "kernel_ms_per_launch": kern_ms,
+        "note": "duration = CUDA-event time of the dominant kernel per launch"
+                + (" (timed region / launches, inter-launch gaps included)" if wl.use_graph else ""),
     }
-    # ---------------- CPU baseline on this box's host cores (bounded sample; oracle = checker only)
+    ipu = getattr(wl, "inst_per_unit", None)
+    if ipu:  # the second roofline of the north star: warp-instruction issue (148 SMs x 4 schedulers x clock)
+        issue_peak = 148 * 4 * sm_mhz * 1e6
+        t_math = ipu * wl.units / 32.0 / issue_peak
+        t_hbm = wl.alg_bytes * wl.units / (peak * 1e9)
+        roofline["math"] = {
+            "warp_inst_per_unit": ipu, "issue_peak_warp_inst_per_s": issue_peak, "t_math_us": t_math * 1e6,
+            "t_hbm_us": t_hbm * 1e6, "slower_bound": "math" if t_math > t_hbm else "hbm",
+            "frac_of_slower_bound": max(t_math, t_hbm) / (kern_ms * 1e-3),
+        }
+    cfg = {"workload": wl.name}
+    cfg.update(wl.config())
+    cfg["launch"] = (f"K={K} steps captured in one CUDA graph (programmatic dependent launches), replayed once" if wl.use_graph
+                     else f"K={K} steps launched back to back on one stream") + "; CUDA events on the launching stream"
+    cfg["parallelism"] = f"batch sharded over {world} rank(s), no data-path collective; NCCL all-reduce of the 2-double statistics at the end"
+    line = {
+        "metric": wl.metric, "value": value, "unit": wl.unit, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": wl.scaling, "vs_baseline": None,
+        "dtype": wl.dtype, "data": "synthetic", "config": cfg, "roofline": roofline,
+        "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+    }
+    # ---------------- CPU baseline on this box's host cores (bounded sample; oracle = the thing timed beside us)
     if world == 1 and not args.no_cpu:
-        rate1, wall1 = cpu_step_rate(1 << 20, 16, 1)
+        n_s = wl.cpu_sample
+        reps = 8 if wl.cpu_kind in ("c2", "c1") else 2
+        rate1, wall1 = cpu_rate(wl.cpu_kind, n_s, reps, 1)
         line["cpu_baseline"] = {
-            "value": rate1,
-            "unit": UNIT,
-            "cores": 1,
-            "kind": "port",
-            "sample": f"2^20 envs x 16 steps of the numpy oracle port (vectorised restatement of base_control.py:61-83), {wall1:.1f} s",
+            "value": rate1, "unit": wl.unit, "cores": 1, "kind": "port",
+            "sample": f"{n_s} units x {reps} passes of the numpy oracle port (oracle/emei_oracle.py, kind={wl.cpu_kind}), {wall1:.1f} s",
         }
     print(json.dumps(line), flush=True)
     if world > 1:
@@ -346,13 +669,18 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--ring", type=int, default=8)
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--ring", type=int, default=0)
     ap.add_argument("--e2e-steps", type=int, default=30)
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
+    if args.steps is None:
+        args.steps = 2000 if WORKLOADS[args.workload].use_graph else 20
+        if args.impl == "reference":
+            args.steps = 20
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -29,6 +29,9 @@ ACTION_DISCRETE_U8, ACTION_DISCRETE_I32, ACTION_DISCRETE_I64, ACTION_CONTINUOUS_
 ) = range(13)
 
 
+SUMSQ_WORKSPACE_BYTES = (148 * 8 + 1) * 8  # EMEI_SUMSQ_WORKSPACE_BYTES
+
+
 class EmeiB200Error(RuntimeError):
     pass
 
@@ -93,7 +96,7 @@ _PROTOTYPES = {
     "emei_cartpole_step": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int64, POINTER(CartPoleParams), _P]),
     "emei_charged_ball_step": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int64, POINTER(ChargedBallParams), _P]),
     "emei_reward_terminal": (c_int, [_P, _P, _P, _P, _P, _P, c_int64, POINTER(ScoringParams), _P]),
-    "emei_sumsq": (c_int, [_P, c_int64, _P, _P]),
+    "emei_sumsq": (c_int, [_P, c_int64, _P, _P, _P]),
     "emei_init_uniform": (c_int, [_P, c_int64, c_int32, c_double, c_double, c_int32, c_uint64, c_uint64, _P]),
     "emei_init_gaussian": (c_int, [_P, c_int64, c_int32, POINTER(c_double), POINTER(c_double), c_uint64, c_uint64, _P]),
     "emei_init_charged_ball": (c_int, [_P, _P, _P, c_int64, c_double, c_uint64, c_uint64, _P]),

@@ -187,6 +187,20 @@ class EmeiEnv(Freezable):
         assert self.frozen
         raise NotImplementedError
 
+    # ------------------------------------------------------------------ host-side callers
+    def step_host(self, action):
+        """``step`` for callers that live on the host (the reference's numpy world): ``action`` is a
+        numpy array / CPU tensor; returns numpy ``(obs, reward, terminated, False, {})``.
+
+        Per call: pinned H2D copy of the actions, the step kernel, D2H copies of obs / reward / done
+        into pinned staging buffers, one stream synchronise.  The returned arrays are views of those
+        staging buffers (valid until the next ``step_host``)."""
+        from .engine import HostStaging
+
+        if getattr(self, "_staging", None) is None:
+            self._staging = HostStaging(self)
+        return self._staging.step(action)
+
     # ------------------------------------------------------------------ seeding (gym.Env.reset(seed=))
     def _reseed(self, seed):
         if seed is not None:

@@ -535,8 +535,14 @@ int reward_terminal(const R* obs, const R* pre_obs, R* reward, uint8_t* done, do
 // =============================================================================================
 // sum of squares (batch-wide control cost, hopper.py:98 / half_cheetah.py:61)
 // =============================================================================================
+constexpr int kSumsqMaxBlocks = kNumSMs * 8;
+
+// Deterministic (bit-reproducible run to run) single-launch reduction: every CTA writes its partial
+// to workspace[1 + blockIdx]; the last CTA to arrive (ticket counter in workspace[0], left at zero
+// again for the next call) adds the partials in index order.  No floating-point atomics: the result
+// does not depend on CTA scheduling, so get_batch_reward and get_batch_reward_terminal agree bitwise.
 template <typename R>
-__global__ void __launch_bounds__(kBlock) sumsq_kernel(const R* __restrict__ x, int64_t n, double* out) {
+__global__ void __launch_bounds__(kBlock) sumsq_kernel(const R* __restrict__ x, int64_t n, double* out, double* workspace) {
   // grid-stride, 128-bit loads on the aligned body; double accumulation
   constexpr int V = 16 / sizeof(R);
   const int64_t nvec = n / V;
@@ -553,30 +559,55 @@ __global__ void __launch_bounds__(kBlock) sumsq_kernel(const R* __restrict__ x, 
     acc += t * t;
   }
   __shared__ double s_acc[kBlock / 32];
+  __shared__ bool s_last;
   acc = warp_sum(acc);
   if ((threadIdx.x & 31) == 0) s_acc[threadIdx.x >> 5] = acc;
   __syncthreads();
   if (threadIdx.x < 32) {
     double t = threadIdx.x < kBlock / 32 ? s_acc[threadIdx.x] : 0.0;
     t = warp_sum(t);
-    if (threadIdx.x == 0) atomicAdd(out, t);
+    if (threadIdx.x == 0) {
+      workspace[1 + blockIdx.x] = t;
+      __threadfence();
+      unsigned long long* ticket = reinterpret_cast<unsigned long long*>(workspace);
+      s_last = atomicAdd(ticket, 1ull) == gridDim.x - 1;
+    }
+  }
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    double t = 0.0;
+    for (int j = threadIdx.x; j < static_cast<int>(gridDim.x); j += kBlock) t += __ldcg(workspace + 1 + j);
+    t = warp_sum(t);
+    if ((threadIdx.x & 31) == 0) s_acc[threadIdx.x >> 5] = t;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      double u = threadIdx.x < kBlock / 32 ? s_acc[threadIdx.x] : 0.0;
+      u = warp_sum(u);
+      if (threadIdx.x == 0) {
+        *out = u;
+        *reinterpret_cast<unsigned long long*>(workspace) = 0ull;  // ready for the next call
+      }
+    }
   }
 }
 
 template <typename R>
-int sumsq(const R* x, int64_t n_elems, double* out, emei_stream_t stream) {
+int sumsq(const R* x, int64_t n_elems, double* out, double* workspace, emei_stream_t stream) {
   if (n_elems < 0) return EMEI_ERR_BAD_SIZE;
   EMEI_CHECK_PTR(out);
+  EMEI_CHECK_PTR(workspace);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  cudaError_t e = cudaMemsetAsync(out, 0, sizeof(double), s);
-  if (e != cudaSuccess) return static_cast<int>(e);
-  if (n_elems == 0) return EMEI_OK;
+  if (n_elems == 0) {
+    cudaError_t e = cudaMemsetAsync(out, 0, sizeof(double), s);
+    return e == cudaSuccess ? EMEI_OK : static_cast<int>(e);
+  }
   EMEI_CHECK_PTR(x);
   EMEI_CHECK_ALIGN16(x);
   constexpr int V = 16 / sizeof(R);
   int64_t want = (n_elems / V + kBlock - 1) / kBlock;
-  int grid = static_cast<int>(want < 1 ? 1 : (want > kNumSMs * 8 ? kNumSMs * 8 : want));
-  sumsq_kernel<R><<<grid, kBlock, 0, s>>>(x, n_elems, out);
+  int grid = static_cast<int>(want < 1 ? 1 : (want > kSumsqMaxBlocks ? kSumsqMaxBlocks : want));
+  sumsq_kernel<R><<<grid, kBlock, 0, s>>>(x, n_elems, out, workspace);
   return launch_status();
 }
 

@@ -241,7 +241,10 @@ def score(env, params: _lib.ScoringParams, obs, pre_obs=None, action=None, want=
         if tuple(p.shape) != tuple(o.shape) or a.shape[0] != b:
             raise ValueError("obs / pre_obs / action batch shapes disagree")
         sumsq = torch.empty(1, dtype=torch.float64, device=env.device)
-        env._call("emei_sumsq", a.data_ptr(), a.numel(), sumsq.data_ptr(), env._stream())
+        ws = getattr(env, "_sumsq_ws", None)
+        if ws is None:  # zero-filled once; the kernel leaves its ticket counter at zero
+            ws = env._sumsq_ws = torch.zeros(_lib.SUMSQ_WORKSPACE_BYTES // 8, dtype=torch.float64, device=env.device)
+        env._call("emei_sumsq", a.data_ptr(), a.numel(), sumsq.data_ptr(), ws.data_ptr(), env._stream())
         if getattr(env, "ctrl_cost_scope", "global") == "global":
             from .dist import all_reduce_sum_
 
@@ -259,6 +262,32 @@ def score(env, params: _lib.ScoringParams, obs, pre_obs=None, action=None, want=
         sumsq.data_ptr() if sumsq is not None else None, b, ctypes.byref(params), env._stream(),
     )
     return reward, done.view(torch.bool), was_np
+
+
+def time_fused_scoring(env, obs, pre_obs, action, reps=10):
+    """CUDA-event duration (ms per launch) of the fused reward+terminal kernel alone, for the roofline
+    of bench.py: the sum-of-squares pre-pass runs once outside the timed launches."""
+    params = env._scoring_params()
+    b = obs.shape[0]
+    sumsq = torch.zeros(1, dtype=torch.float64, device=env.device)
+    ws = torch.zeros(_lib.SUMSQ_WORKSPACE_BYTES // 8, dtype=torch.float64, device=env.device)
+    env._call("emei_sumsq", action.data_ptr(), action.numel(), sumsq.data_ptr(), ws.data_ptr(), env._stream())
+    reward = torch.empty((b, 1), dtype=env.dtype, device=env.device)
+    done = torch.empty((b, 1), dtype=torch.uint8, device=env.device)
+
+    def launch():
+        env._call("emei_reward_terminal", obs.data_ptr(), pre_obs.data_ptr(), reward.data_ptr(), done.data_ptr(), None,
+                  sumsq.data_ptr(), b, ctypes.byref(params), env._stream())
+
+    launch()
+    torch.cuda.synchronize(env.device)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        launch()
+    e1.record()
+    torch.cuda.synchronize(env.device)
+    return e0.elapsed_time(e1) / reps
 
 
 class HostStaging:

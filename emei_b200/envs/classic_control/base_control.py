@@ -94,16 +94,3 @@ class BaseControlEnv(EmeiEnv):
         a = normalise_action(self, action, self._is_continuous())
         obs, reward, terminal = self._engine.step(a, self.copy_outputs)
         return obs, reward, terminal, False, {}
-
-    def step_host(self, action):
-        """``step`` for callers that live on the host (the reference's numpy world): ``action`` is a
-        numpy array / CPU tensor; returns numpy ``(obs, reward, terminated, False, {})``.
-
-        Per call: one pinned H2D copy of the actions, one kernel launch, three D2H copies into pinned
-        staging buffers, one stream synchronise.  The returned arrays are views of those staging
-        buffers (valid until the next ``step_host``)."""
-        from ...engine import HostStaging
-
-        if getattr(self, "_staging", None) is None:
-            self._staging = HostStaging(self)
-        return self._staging.step(action)

@@ -154,10 +154,16 @@ int emei_reward_terminal_f32(const float* obs, const float* pre_obs, float* rewa
 int emei_reward_terminal_f64(const double* obs, const double* pre_obs, double* reward, uint8_t* done, double* stats,
                              const double* sumsq, int64_t n, const emei_scoring_params* p, emei_stream_t stream);
 
-/* sum of squares of n_elems values, accumulated in double into *out (device); *out is zeroed first.
- * Replaces np.sum(np.square(action)) (hopper.py:98, half_cheetah.py:61). */
-int emei_sumsq_f32(const float* x, int64_t n_elems, double* out, emei_stream_t stream);
-int emei_sumsq_f64(const double* x, int64_t n_elems, double* out, emei_stream_t stream);
+/* sum of squares of n_elems values, accumulated in double, written to *out (device).
+ * Replaces np.sum(np.square(action)) (hopper.py:98, half_cheetah.py:61).  One launch, deterministic:
+ * per-CTA partials go to `workspace` and the last CTA adds them in index order (no floating-point
+ * atomics), so repeated calls on the same data return the same bits.
+ *   workspace : DEVICE buffer of EMEI_SUMSQ_WORKSPACE_BYTES bytes, 8-byte aligned, zero-filled ONCE
+ *               by the caller before its first use (the kernel leaves its ticket counter at zero);
+ *               not shared between concurrent streams. */
+#define EMEI_SUMSQ_WORKSPACE_BYTES ((148 * 8 + 1) * 8)
+int emei_sumsq_f32(const float* x, int64_t n_elems, double* out, double* workspace, emei_stream_t stream);
+int emei_sumsq_f64(const double* x, int64_t n_elems, double* out, double* workspace, emei_stream_t stream);
 
 /* ---- batched initial-state sampling (counter-based Philox4x32-10) -------------- */
 /* value(env, column) depends only on (seed, env_offset + row, column): independent of sharding. */
