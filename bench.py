@@ -354,6 +354,8 @@ class ChargedBall(Workload):
         import emei_b200 as E
         from emei_b200.dist import shard_range
 
+        if self.args.total_log2:
+            self.total = 1 << self.args.total_log2
         b, e = shard_range(self.total, self.rank, self.world)
         self.units = e - b
         self.env = E.make("ChargedBallCentering-v0", num_envs=self.units, dtype=torch.float32, device=self.dev, env_offset=b)
@@ -676,6 +678,7 @@ def main():
     ap.add_argument("--ring", type=int, default=0)
     ap.add_argument("--e2e-steps", type=int, default=30)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--total-log2", type=int, default=0, help="c4 only: log2 of the total env count (default 26)")
     args = ap.parse_args()
     if args.steps is None:
         args.steps = 2000 if WORKLOADS[args.workload].use_graph else 20

@@ -25,6 +25,27 @@ inline int grid_for(int64_t n, int per_block) {
   return static_cast<int>(g);
 }
 
+// persistent launch: enough CTAs to cover n once, capped at ctas_per_sm resident CTAs on every SM
+// (the kernels grid-stride over the rest, so every SM carries the same number of units +-1)
+inline int persistent_grid(int64_t n, int per_block, int ctas_per_sm) {
+  const int64_t want = (n + per_block - 1) / per_block;
+  const int64_t cap = static_cast<int64_t>(kNumSMs) * ctas_per_sm;
+  return static_cast<int>(want < 1 ? 1 : (want > cap ? cap : want));
+}
+
+// persistent grid sized by the kernel's ACTUAL residency (registers / shared memory decide how many
+// CTAs fit on an SM; a grid larger than one resident wave would run a ragged second wave).  The
+// occupancy query result is cached per kernel instantiation (immutable after first use).
+template <typename... KArgs>
+inline int resident_grid(void (*kernel)(KArgs...), int64_t n) {
+  static const int per_sm = [kernel]() {
+    int nb = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, kBlock, 0) != cudaSuccess || nb < 1) nb = 4;
+    return nb;
+  }();
+  return persistent_grid(n, kBlock, per_sm);
+}
+
 // ---------------------------------------------------------------------------------------------
 // Programmatic dependent launch (sm_90+): a rollout is a chain of short (~10 us) step kernels on one
 // stream, so the launch latency between them is a visible fraction of the step.  Kernels launched
@@ -53,13 +74,6 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), int grid, int block, cud
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
-// persistent launch: enough CTAs to cover n once, capped at ctas_per_sm resident CTAs on every SM
-// (the kernels grid-stride over the rest, so every SM carries the same number of units +-1)
-inline int persistent_grid(int64_t n, int per_block, int ctas_per_sm) {
-  const int64_t want = (n + per_block - 1) / per_block;
-  const int64_t cap = static_cast<int64_t>(kNumSMs) * ctas_per_sm;
-  return static_cast<int>(want < 1 ? 1 : (want > cap ? cap : want));
-}
 
 // ---------------------------------------------------------------------------------------------
 // vector types: one env row (4 scalars) per 128-bit (f32) / 2 x 128-bit (f64) access

@@ -118,6 +118,28 @@ class CartPoleEngine:
         self._cur = nxt
         return (obs if obs is not None else dst), reward, done.view(torch.bool)
 
+    def step_range(self, lo: int, hi: int, action: torch.Tensor, reward: torch.Tensor, done: torch.Tensor, obs_out):
+        """Launch the step kernel for envs [lo, hi) only (src -> dst of the CURRENT ping-pong pair, no flip):
+        the building block of the chunked host pipeline.  Call ``flip()`` once all ranges are launched."""
+        env = self.env
+        self._alloc()
+        src, dst = self._bufs[self._cur], self._bufs[1 - self._cur]
+        if self.separate_obs and obs_out is None:
+            obs_out = self._obs[1 - self._cur]
+        self.params.action_kind = _ACTION_KIND[action.dtype]
+        es, ea = src.element_size() * 4, action.element_size()
+        env._call(
+            "emei_cartpole_step",
+            src.data_ptr() + lo * es, dst.data_ptr() + lo * es,
+            (obs_out.data_ptr() + lo * es) if obs_out is not None else None, action.data_ptr() + lo * ea,
+            reward.data_ptr() + lo * reward.element_size(), done.data_ptr() + lo, env.stats.data_ptr(), hi - lo,
+            ctypes.byref(self.params), env._stream(),
+        )
+        return obs_out if obs_out is not None else dst
+
+    def flip(self):
+        self._cur = 1 - self._cur
+
     def next_obs_stateless(self, obs: torch.Tensor, action: torch.Tensor):
         """get_batch_next_obs: one dynamics step from caller-supplied observations (any batch size);
         the engine's own state is untouched."""
@@ -201,6 +223,21 @@ class ChargedBallEngine:
         )
         obs = self.free.clone() if copy_obs else self.free
         return obs, reward, done.view(torch.bool)
+
+    def step_range(self, lo: int, hi: int, action: torch.Tensor, reward: torch.Tensor, done: torch.Tensor, obs_out):
+        env = self.env
+        self.params.action_kind = _ACTION_KIND[action.dtype]
+        es = self.free.element_size()
+        env._call(
+            "emei_charged_ball_step",
+            self.on_circle.data_ptr() + lo, self.circle.data_ptr() + lo * 2 * es, self.free.data_ptr() + lo * 4 * es,
+            action.data_ptr() + lo * action.element_size(), reward.data_ptr() + lo * es, done.data_ptr() + lo,
+            env.stats.data_ptr(), hi - lo, ctypes.byref(self.params), env._stream(),
+        )
+        return self.free
+
+    def flip(self):
+        pass
 
     def snapshot(self):
         out = []
@@ -291,32 +328,68 @@ def time_fused_scoring(env, obs, pre_obs, action, reps=10):
 
 
 class HostStaging:
-    """Pinned host buffers + the copy choreography of ``step_host`` (end-to-end path with HOST inputs
-    and outputs).  Works for any env whose ``step`` returns ``(obs, reward, done)`` device tensors."""
+    """Pinned host buffers + the copy choreography of ``step_host`` (the end-to-end path with HOST
+    inputs and outputs).  The env batch is cut into ``chunks`` contiguous ranges, each on its own
+    stream: H2D(actions) -> step kernel on the range -> D2H(obs, reward, done).  Envs are independent,
+    so range k+1's upload and range k-1's download overlap range k's kernel, and PCIe runs in both
+    directions at once.  One host synchronisation per call."""
 
-    def __init__(self, env):
+    def __init__(self, env, chunks: int = 4):
         self.env = env
         n = env.num_envs
         cont = len(env.action_space.shape) > 0
+        dev = env.device
         self.a_host = torch.empty((n,), dtype=torch.float32 if cont else torch.uint8).pin_memory()
-        self.a_dev = torch.empty_like(self.a_host, device=env.device)
+        self.a_dev = torch.empty_like(self.a_host, device=dev)
         obs_dim = env.observation_space.shape[0]
         self.obs_host = torch.empty((n, obs_dim), dtype=env.dtype).pin_memory()
         self.rew_host = torch.empty((n, 1), dtype=env.dtype).pin_memory()
         self.done_host = torch.empty((n, 1), dtype=torch.bool).pin_memory()
+        self.rew_dev = torch.empty((n, 1), dtype=env.dtype, device=dev)
+        self.done_dev = torch.empty((n, 1), dtype=torch.uint8, device=dev)
         self.h2d_bytes = self.a_host.numel() * self.a_host.element_size()
         self.d2h_bytes = sum(t.numel() * t.element_size() for t in (self.obs_host, self.rew_host, self.done_host))
+        chunks = max(1, min(int(chunks), n // 131072 or 1))  # small batches: one range (latency-bound anyway)
+        edges = [round(i * n / chunks) for i in range(chunks + 1)]
+        self.ranges = [(edges[i], edges[i + 1]) for i in range(chunks) if edges[i + 1] > edges[i]]
+        self.streams = [torch.cuda.Stream(dev) for _ in self.ranges]
+        self.done_host_u8 = self.done_host.view(torch.uint8)
 
     def step(self, action):
         env = self.env
+        eng = env._engine
+        assert eng is not None and eng.has_state, "Call reset before using step method."
         a = torch.as_tensor(action)
         if a.is_cuda:
             raise TypeError("step_host takes host actions; use step() for device tensors")
-        self.a_host.copy_(a.reshape(-1))  # host-side cast into the pinned staging buffer (uint8 / float32)
-        self.a_dev.copy_(self.a_host, non_blocking=True)
-        obs, reward, done, trunc, info = env.step(self.a_dev)
-        self.obs_host.copy_(obs, non_blocking=True)
-        self.rew_host.copy_(reward, non_blocking=True)
-        self.done_host.copy_(done, non_blocking=True)
-        torch.cuda.current_stream(env.device).synchronize()
-        return self.obs_host.numpy(), self.rew_host.numpy(), self.done_host.numpy(), trunc, info
+        a = a.reshape(-1)
+        if a.dtype == self.a_host.dtype and a.is_pinned() and a.is_contiguous() and a.numel() == self.a_host.numel():
+            a_src = a  # already page-locked in the wire dtype: DMA straight from the caller's buffer
+        else:
+            self.a_host.copy_(a)  # host-side cast into the pinned staging buffer (uint8 / float32)
+            a_src = self.a_host
+        cur = torch.cuda.current_stream(env.device)
+        if len(self.ranges) == 1:  # small batch: latency-bound, no side streams
+            self.a_dev.copy_(a_src, non_blocking=True)
+            obs = eng.step_range(0, env.num_envs, self.a_dev, self.rew_dev, self.done_dev, None)
+            eng.flip()
+            self.obs_host.copy_(obs, non_blocking=True)
+            self.rew_host.copy_(self.rew_dev, non_blocking=True)
+            self.done_host_u8.copy_(self.done_dev, non_blocking=True)
+            cur.synchronize()
+            return self.obs_host.numpy(), self.rew_host.numpy(), self.done_host.numpy(), False, {}
+        start = torch.cuda.Event()
+        start.record(cur)
+        for (lo, hi), st in zip(self.ranges, self.streams):
+            with torch.cuda.stream(st):
+                st.wait_event(start)  # everything queued before this call (reset, set_state, ...) is visible
+                self.a_dev[lo:hi].copy_(a_src[lo:hi], non_blocking=True)
+                obs = eng.step_range(lo, hi, self.a_dev, self.rew_dev, self.done_dev, None)
+                self.obs_host[lo:hi].copy_(obs[lo:hi], non_blocking=True)
+                self.rew_host[lo:hi].copy_(self.rew_dev[lo:hi], non_blocking=True)
+                self.done_host_u8[lo:hi].copy_(self.done_dev[lo:hi], non_blocking=True)
+        eng.flip()
+        for st in self.streams:
+            cur.wait_stream(st)
+        cur.synchronize()
+        return self.obs_host.numpy(), self.rew_host.numpy(), self.done_host.numpy(), False, {}

@@ -655,3 +655,38 @@ def test_empty_and_ragged_batches():
     for n in (1, 5, 1025):
         r, d = env.get_batch_reward_terminal(np.zeros((n, 18)), np.zeros((n, 18)), np.ones((n, 6)))
         assert r.shape == (n, 1) and close64(r, np.full((n, 1), -0.1 * 6 * n))
+
+
+# ================================================================================================
+# step_host: the end-to-end host path (chunked multi-stream pipeline) must equal step() bit for bit
+# ================================================================================================
+@pytest.mark.parametrize("n", (1000, 300_000))
+@pytest.mark.parametrize("env_id", ("ContinuousCartPoleSwingUp-v0", "CartPoleBalancing-v0", "BoundaryInvertedPendulumSwingUp-v0",
+                                    "ChargedBallCentering-v0"))
+def test_step_host_equals_step(env_id, n):
+    rng = np.random.default_rng(5)
+    a = E.make(env_id, num_envs=n, dtype=torch.float32, freq_rate=2)
+    b = E.make(env_id, num_envs=n, dtype=torch.float32, freq_rate=2)
+    a.reset(seed=11)
+    b.reset(seed=11)
+    cont = len(a.action_space.shape) > 0
+    for t in range(3):
+        if cont:
+            lo, hi = float(a.action_space.low[0]), float(a.action_space.high[0])
+            act = rng.uniform(lo, hi, size=n).astype(np.float32)
+        else:
+            act = rng.integers(0, 2, size=n).astype(np.uint8)
+        o1, r1, d1, _, _ = a.step(torch.as_tensor(act).cuda())
+        o2, r2, d2, tr, info = b.step_host(act)
+        assert tr is False and info == {}
+        assert isinstance(o2, np.ndarray) and o2.shape == (n, 4) and r2.shape == (n, 1) and d2.dtype == np.bool_
+        assert np.array_equal(o1.cpu().numpy(), o2, equal_nan=True)
+        assert np.array_equal(r1.cpu().numpy(), r2, equal_nan=True)
+        assert np.array_equal(d1.cpu().numpy(), d2)
+    sa, sb = a.state, b.state
+    if isinstance(sa, dict):
+        for k in sa:
+            assert torch.equal(sa[k], sb[k])
+    else:
+        assert torch.equal(sa, sb)
+    assert a.read_stats()[1] == b.read_stats()[1]

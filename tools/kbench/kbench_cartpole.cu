@@ -44,6 +44,63 @@ compute_kernel(float* out, uint32_t n, const CartPoleF32Consts k) {
   if (acc == 12345.678f) out[0] = acc;
 }
 
+// EXPERIMENT: two envs per thread per iteration (two independent dependency chains interleaved by
+// the compiler), cp.async ring of S stages x 2 envs.
+template <int MINB, int S>
+__global__ void __launch_bounds__(kBlock, MINB)
+cartpole_ilp2_kernel(const float4* state_in, float4* state_out, const float* __restrict__ act, float* __restrict__ reward,
+                     uint8_t* __restrict__ done, double* stats, uint32_t n, const CartPoleF32Consts k) {
+  __shared__ float4 s_state[S][2][kBlock];
+  __shared__ float s_act[S][2][kBlock];
+  const uint32_t tid = threadIdx.x;
+  const uint32_t half = gridDim.x * kBlock;   // env B of a pair sits `half` after env A
+  const uint32_t stride = 2 * half;
+  uint32_t i = blockIdx.x * kBlock + tid;
+  float r_acc = 0.f; unsigned d_cnt = 0;
+  auto stage_in = [&](int slot, uint32_t idx) {
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const uint32_t j = idx + e * half;
+      if (j < n) { cp_async<16>(&s_state[slot][e][tid], state_in + j); cp_async<4>(&s_act[slot][e][tid], act + j); }
+    }
+    cp_async_commit();
+  };
+  pdl_trigger(); pdl_wait();
+#pragma unroll
+  for (int d = 0; d < S; ++d) stage_in(d, i + d * stride);
+  int slot = 0;
+  while (i < n) {
+    cp_async_wait<S - 1>();
+    float4 y[2]; float f_mt[2]; float th_max[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) { y[e] = s_state[slot][e][tid]; f_mt[e] = (k.force_mag * s_act[slot][e][tid]) * k.k.inv_mt; th_max[e] = 0.f; }
+#pragma unroll
+    for (int sub = 0; sub < 4; ++sub) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        f32::cartpole_substep<false>(y[e].x, y[e].y, y[e].z, y[e].w, f_mt[e], 1.0f, k.k);
+        th_max[e] = fmaxf(th_max[e], fabsf(y[e].z));
+      }
+    }
+    stage_in(slot, i + S * stride);
+    slot = slot + 1 == S ? 0 : slot + 1;
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const uint32_t j = i + e * half;
+      if (j < n) {
+        if (!(th_max[e] <= f32::kSinCosSaneMax)) { y[e] = state_in[j]; integrate<false, 4, true>(y[e], f_mt[e], 1.0f, k); }
+        state_out[j] = y[e];
+        const float rew = fmaf(f32::cos_fast(y[e].z), 0.5f, 0.5f);
+        const unsigned d = fabsf(y[e].x) < k.x_thr ? 0u : 1u;
+        reward[j] = rew; done[j] = (uint8_t)d; r_acc += rew; d_cnt += d;
+      }
+    }
+    i += stride;
+  }
+  cp_async_wait<0>();
+  block_stats_accumulate_counts(stats, (double)r_acc, d_cnt);
+}
+
 struct Ring {
   std::vector<float*> in, out, act, rew; std::vector<uint8_t*> done;
 };
@@ -86,6 +143,25 @@ void run_cartpole(const char* name, Ring& R, uint32_t n, int K, cudaStream_t s, 
     auto kern = cartpole_step_f32_kernel<false, EMEI_ACTION_CONTINUOUS_F32, FR, MINB, false, S, DBG>;
     if (PDL) launch_pdl(kern, grid, kBlock, s, (const float4*)R.in[j], (float4*)R.out[j], (float4*)nullptr, (const void*)R.act[j], R.rew[j], R.done[j], stats, n, k);
     else kern<<<grid, kBlock, 0, s>>>((const float4*)R.in[j], (float4*)R.out[j], nullptr, R.act[j], R.rew[j], R.done[j], stats, n, k);
+  };
+  float us = time_graph(launch, K, s);
+  CK(cudaGetLastError());
+  printf("%-44s grid=%5d  %7.2f us/launch  %6.1f Genv-steps/s  %6.0f GB/s (41 B/env)\n", name, grid, us, n / us * 1e-3, 41.0 * n / us * 1e-3);
+  cudaFree(stats);
+}
+
+template <int MINB, int S>
+void run_ilp2(const char* name, Ring& R, uint32_t n, int K, cudaStream_t s) {
+  emei_cartpole_params p = {};
+  p.gravity = 9.8; p.mass_pole = 0.1; p.total_mass = 1.1; p.length = 0.5; p.pole_mass_length = 0.05; p.force_mag = 10.0;
+  p.x_threshold = 5.0; p.theta_threshold = 0.2; p.dt = 0.02; p.freq_rate = 4; p.variant = EMEI_CARTPOLE_SWINGUP;
+  CartPoleF32Consts k = make_cartpole_f32_consts(p);
+  int grid = persistent_grid((n + 1) / 2, kBlock, MINB);
+  double* stats; CK(cudaMalloc(&stats, 16)); CK(cudaMemset(stats, 0, 16));
+  const int ring = (int)R.in.size();
+  auto launch = [&](int i) {
+    int j = i % ring;
+    launch_pdl(cartpole_ilp2_kernel<MINB, S>, grid, kBlock, s, (const float4*)R.in[j], (float4*)R.out[j], (const float*)R.act[j], R.rew[j], R.done[j], stats, n, k);
   };
   float us = time_graph(launch, K, s);
   CK(cudaGetLastError());
@@ -148,6 +224,12 @@ int main(int argc, char** argv) {
   run_cartpole<4, 0, true>("cartpole fr-runtime minb4 pdl", R, n, K, s);
   run_cartpole<5, 0, true>("cartpole fr-runtime minb5 pdl", R, n, K, s);
   run_cartpole<8, 0, true>("cartpole fr-runtime minb8 pdl", R, n, K, s);
+  run_ilp2<4, 2>("ILP2 minb4 S2", R, n, K, s);
+  run_ilp2<4, 3>("ILP2 minb4 S3", R, n, K, s);
+  run_ilp2<3, 2>("ILP2 minb3 S2", R, n, K, s);
+  run_ilp2<3, 3>("ILP2 minb3 S3", R, n, K, s);
+  run_ilp2<2, 3>("ILP2 minb2 S3", R, n, K, s);
+  run_ilp2<2, 4>("ILP2 minb2 S4", R, n, K, s);
   run_cartpole<4, 4, true, 4>("cartpole fr4 minb4 S4", R, n, K, s);
   run_cartpole<4, 4, true, 4, 1>("cartpole fr4 minb4 S4 NO-STORE", R, n, K, s);
   run_cartpole<4, 4, true, 4, 2>("cartpole fr4 minb4 S4 NO-LOAD", R, n, K, s);
