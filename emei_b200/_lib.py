@@ -90,6 +90,27 @@ class ScoringParams(Structure):
     ]
 
 
+class RolloutParams(Structure):
+    _fields_ = [
+        ("horizon", c_int32),
+        ("max_episode_steps", c_int32),
+        ("auto_reset", c_int32),
+        ("random_policy", c_int32),
+        ("init_kind", c_int32),
+        ("init_pi_column", c_int32),
+        ("seed_reset", c_uint64),
+        ("seed_action", c_uint64),
+        ("env_offset", c_uint64),
+        ("t0", c_uint64),
+        ("init_low", c_double),
+        ("init_high", c_double),
+        ("init_mean", c_double * 4),
+        ("init_sigma", c_double * 4),
+        ("action_low", c_double),
+        ("action_high", c_double),
+    ]
+
+
 _P = c_void_p
 _PROTOTYPES = {
     # name: (restype, argtypes)
@@ -102,6 +123,7 @@ _PROTOTYPES = {
     "emei_init_charged_ball": (c_int, [_P, _P, _P, c_int64, c_double, c_uint64, c_uint64, _P]),
 }
 _PLAIN = {
+    "emei_cartpole_rollout_f32": (c_int, [_P] * 12 + [c_int64, POINTER(CartPoleParams), POINTER(RolloutParams), _P]),
     "emei_snapshot_copy": (c_int, [_P, _P, c_int64, _P]),
     "emei_stats_reset": (c_int, [_P, _P]),
     "emei_version": (c_int, []),

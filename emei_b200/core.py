@@ -187,6 +187,53 @@ class EmeiEnv(Freezable):
         assert self.frozen
         raise NotImplementedError
 
+    # ------------------------------------------------------------------ fused rollouts
+    def rollout(self, horizon: int, actions=None, record: bool = False, auto_reset: bool = True, max_episode_steps=None):
+        """``horizon`` steps of every env in ONE kernel launch: the batched counterpart of the reference's
+        collection loop (zoo/util.py:33-93) with gym's TimeLimit (``max_episode_steps`` of the registry,
+        register_env.py) and the per-episode ``reset()`` done on the device.
+
+        actions: ``[horizon, num_envs]`` tensor / numpy (teacher-forced policy) or None for the uniform
+        random policy (``env.action_space.sample()``, zoo/util.py:57).
+        record:  also return the transitions in the reference's dataset layout (zoo/util.py:62-67):
+        ``observations, next_observations [T,B,4]; actions, rewards [T,B]; dones, timeouts bool[T,B]``.
+        Returns a dict with those records (if any) and ``stats``: device double[6] = [sum of rewards,
+        #terminated, #truncated, #episodes finished, sum of finished returns, sum of finished lengths];
+        ``rollout_info(stats)`` turns it into the reference's avg_reward / avg_length / total_episode_num."""
+        eng = getattr(self, "_ensure_engine", lambda: self._engine)()
+        if eng is None or not hasattr(eng, "rollout"):
+            raise NotImplementedError(f"{type(self).__name__} has no fused rollout kernel")
+        assert self.state is not None, "Call reset before using rollout."
+        rp = self._rollout_params()
+        rp.horizon = int(horizon)
+        mes = getattr(self, "max_episode_steps", 0) if max_episode_steps is None else max_episode_steps
+        rp.max_episode_steps = int(mes or 0)
+        rp.auto_reset = int(bool(auto_reset))
+        rp.random_policy = int(actions is None)
+        rp.env_offset = int(getattr(self, "env_offset", 0))
+        rp.seed_reset = (self._seed * 0x9E3779B97F4A7C15 + 0x5851F42D4C957F2D) & 0xFFFFFFFFFFFFFFFF
+        rp.seed_action = (self._seed * 0xD1B54A32D192ED03 + 0x14057B7EF767814F) & 0xFFFFFFFFFFFFFFFF
+        a = None
+        if actions is not None:
+            a, _ = self._to_device(actions)
+            if a.dtype == torch.bool:
+                a = a.view(torch.uint8)
+        stats = torch.zeros(6, dtype=torch.float64, device=self.device)
+        out = eng.rollout(rp, a, bool(record), stats)
+        out["stats"] = stats
+        return out
+
+    @staticmethod
+    def rollout_info(stats) -> dict:
+        """zoo/util.py:87-91 (one device->host read)."""
+        r_sum, n_term, n_trunc, n_fin, fin_ret, fin_len = [float(v) for v in stats.tolist()]
+        n = max(n_fin, 1.0)
+        return dict(avg_reward=fin_ret / n, avg_length=fin_len / n, total_episode_num=int(n_fin), reward_sum=r_sum,
+                    terminated=int(n_term), truncated=int(n_trunc))
+
+    def _rollout_params(self):
+        raise NotImplementedError(f"{type(self).__name__} has no fused rollout kernel")
+
     # ------------------------------------------------------------------ host-side callers
     def step_host(self, action):
         """``step`` for callers that live on the host (the reference's numpy world): ``action`` is a

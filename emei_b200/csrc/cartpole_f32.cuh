@@ -201,7 +201,7 @@ __global__ void __launch_bounds__(kBlock, MINB)
       }
     } else {
       // observation: theta wrapped to [-pi, pi) (inverted_pendulum.py:45-49)
-      const float th_obs = py_mod(y.y + 3.14159265358979323846f, 6.28318530717958647692f) - 3.14159265358979323846f;
+      const float th_obs = wrap_pi_f32(y.y);
       if constexpr (HAS_OBS) obs_out[i] = make_float4(y.x, th_obs, y.z, y.w);
       const bool finite = isfinite(y.x) && isfinite(th_obs) && isfinite(y.z) && isfinite(y.w);
       const float cy = f32::cos_core(th_obs);  // |th_obs| <= pi (NaN stays NaN)

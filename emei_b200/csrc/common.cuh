@@ -225,6 +225,18 @@ __device__ __forceinline__ float py_mod(float a, float b) {
   return m;
 }
 
+// float32 observation wrap `(theta + pi) % (2 pi) - pi` (inverted_pendulum.py:45-49) by Cody-Waite
+// reduction: exact for |theta| < pi (forming theta + pi in float32 would cost 1.2e-7 of the 1e-6 budget),
+// error <= ulp(theta) beyond.  Result in [-pi_f, pi_f); NaN / Inf -> NaN like the reference.
+__device__ __forceinline__ float wrap_pi_f32(float th) {
+  const float k = rintf(th * 0.15915494309189535f);
+  float r = fmaf(-k, 6.28125f, th);  // 2 pi = 6.28125 + 1.9353071795864769e-3
+  r = fmaf(-k, 1.9353071795864769e-3f, r);
+  r = r >= 3.14159265358979323846f ? r - 6.28318530717958647692f : r;
+  r = r < -3.14159265358979323846f ? r + 6.28318530717958647692f : r;
+  return r;
+}
+
 template <typename R>
 __device__ __forceinline__ bool is_finite(R v) {
   return isfinite(v);

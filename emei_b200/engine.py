@@ -95,6 +95,7 @@ class CartPoleEngine:
             raise ValueError(f"state must have shape {(self.n, 4)}, got {tuple(s.shape)}")
         self._bufs[self._cur].copy_(s)
         self.has_state = True
+        self.new_episodes(reseed=False)
 
     def step(self, action: torch.Tensor, copy_obs: bool):
         env = self.env
@@ -139,6 +140,67 @@ class CartPoleEngine:
 
     def flip(self):
         self._cur = 1 - self._cur
+
+    # ---- fused T-step rollout (emei_cartpole_rollout_f32) ----------------------------------------
+    def _alloc_episode(self):
+        if getattr(self, "ep_step", None) is None:
+            dev = self.env.device
+            self.ep_step = torch.zeros(self.n, dtype=torch.int32, device=dev)
+            self.ep_return = torch.zeros(self.n, dtype=torch.float32, device=dev)
+            self.ep_index = torch.zeros(self.n, dtype=torch.int32, device=dev)
+            self.t_global = 0
+
+    def new_episodes(self, reseed: bool):
+        """called when the env's state is (re)set from outside: every env starts a fresh episode."""
+        if getattr(self, "ep_step", None) is not None:
+            self.ep_step.zero_()
+            self.ep_return.zero_()
+            if reseed:
+                self.ep_index.zero_()
+                self.t_global = 0
+
+    def rollout(self, rp: _lib.RolloutParams, actions, record: bool, rollout_stats: torch.Tensor):
+        env = self.env
+        if env.dtype != torch.float32:
+            raise NotImplementedError("the fused rollout kernel is float32 (use step() for the float64 reference-exact mode)")
+        self._alloc()
+        self._alloc_episode()
+        state = self._bufs[self._cur]
+        T, n, dev = int(rp.horizon), self.n, env.device
+        rp.t0 = self.t_global
+        rec = {}
+        if actions is not None:
+            if tuple(actions.shape[:2]) != (T, n) and tuple(actions.shape) != (T, n):
+                raise ValueError(f"actions must be [horizon={T}, num_envs={n}], got {tuple(actions.shape)}")
+            actions = actions.reshape(T, n).contiguous()
+            self.params.action_kind = _ACTION_KIND[actions.dtype]
+            act_dtype = actions.dtype
+        else:
+            cont = len(env.action_space.shape) > 0
+            act_dtype = torch.float32 if cont else torch.uint8
+            self.params.action_kind = _ACTION_KIND[act_dtype]
+        ptrs = [None] * 6
+        if record:
+            rec = dict(
+                observations=torch.empty((T, n, 4), dtype=torch.float32, device=dev),
+                next_observations=torch.empty((T, n, 4), dtype=torch.float32, device=dev),
+                actions=torch.empty((T, n), dtype=act_dtype, device=dev),
+                rewards=torch.empty((T, n), dtype=torch.float32, device=dev),
+                dones=torch.empty((T, n), dtype=torch.uint8, device=dev),
+                timeouts=torch.empty((T, n), dtype=torch.uint8, device=dev),
+            )
+            ptrs = [rec[k].data_ptr() for k in ("observations", "next_observations", "actions", "rewards", "dones", "timeouts")]
+        with torch.cuda.device(dev):
+            _lib.call(
+                "emei_cartpole_rollout_f32", state.data_ptr(), self.ep_step.data_ptr(), self.ep_return.data_ptr(),
+                self.ep_index.data_ptr(), actions.data_ptr() if actions is not None else None, *ptrs,
+                rollout_stats.data_ptr(), n, ctypes.byref(self.params), ctypes.byref(rp), env._stream(),
+            )
+        self.t_global += T
+        if record:
+            rec["dones"] = rec["dones"].view(torch.bool)
+            rec["timeouts"] = rec["timeouts"].view(torch.bool)
+        return rec
 
     def next_obs_stateless(self, obs: torch.Tensor, action: torch.Tensor):
         """get_batch_next_obs: one dynamics step from caller-supplied observations (any batch size);

@@ -82,6 +82,8 @@ class BaseControlEnv(EmeiEnv):
     def reset(self, *, seed: Optional[int] = None, options: Optional[dict] = None):
         self._reseed(seed)
         self.state = self.get_batch_init_state(self.num_envs)
+        if hasattr(self._engine, "new_episodes"):
+            self._engine.new_episodes(reseed=True)
         return self.state.clone(), {}
 
     def _is_continuous(self) -> bool:

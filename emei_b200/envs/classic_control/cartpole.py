@@ -82,6 +82,15 @@ class BaseCartPoleEnv(BaseControlEnv):
     def get_batch_init_state(self, batch_size):
         raise NotImplementedError
 
+    _init_pi_column = -1
+
+    def _rollout_params(self) -> _lib.RolloutParams:
+        rp = _lib.RolloutParams()
+        rp.init_kind, rp.init_pi_column = 0, self._init_pi_column  # cartpole.py:131-132,153-156
+        rp.init_low, rp.init_high = -0.05, 0.05
+        rp.action_low, rp.action_high = -1.0, 1.0
+        return rp
+
     def _sample_uniform(self, batch_size, pi_column):
         out = torch.empty((batch_size, 4), dtype=self.dtype, device=self.device)
         self._call(
@@ -130,6 +139,8 @@ class CartPoleSwingUpEnv(BaseCartPoleEnv):
     def __init__(self, freq_rate: int = 1, real_time_scale: float = 0.02, integrator: str = "euler", **kwargs):
         super().__init__(freq_rate=freq_rate, real_time_scale=real_time_scale, integrator=integrator, **kwargs)
         self.x_threshold = 5  # cartpole.py:140
+
+    _init_pi_column = 2
 
     def get_batch_init_state(self, batch_size):
         return self._sample_uniform(batch_size, 2)  # cartpole.py:153-156 (theta += pi)

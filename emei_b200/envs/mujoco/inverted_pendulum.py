@@ -64,6 +64,17 @@ class BaseInvertedPendulumEnv(EmeiMujocoEnv):
         p.variant = self._family
         return p
 
+    def _rollout_params(self) -> _lib.RolloutParams:
+        rp = _lib.RolloutParams()
+        rp.init_kind, rp.init_pi_column = 1, -1  # reset_model: init_qpos/qvel + N(0, sigma) (mujoco_env.py:130-140)
+        sp, sv = self._noise_sigmas(self.init_noise_params)
+        mean = np.concatenate([self.init_qpos, self.init_qvel])
+        sigma = np.concatenate([sp, sv])
+        for j in range(4):
+            rp.init_mean[j], rp.init_sigma[j] = float(mean[j]), float(sigma[j])
+        rp.action_low, rp.action_high = float(self.action_space.low[0]), float(self.action_space.high[0])
+        return rp
+
     def _scoring_params(self) -> _lib.ScoringParams:
         p = EmeiMujocoEnv._scoring_params(self)
         p.x_left, p.x_right = float(self.jnt_range[0][0]), float(self.jnt_range[0][1])
@@ -97,6 +108,7 @@ class BaseInvertedPendulumEnv(EmeiMujocoEnv):
             raise NotImplementedError("the analytic inverted pendulum implements integrator='euler' (mujoco_env.py:94-97)")
         self._reseed(seed)
         self.state = self._sample_init_obs(self.num_envs)  # reset_model: mujoco_env.py:130-135
+        self._engine.new_episodes(reseed=True)
         return self.state.clone(), {}
 
     def step(self, action):

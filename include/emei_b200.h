@@ -108,6 +108,41 @@ int emei_cartpole_step_f64(const double* state_in, double* state_out, double* ob
                            double* reward, uint8_t* done, double* stats, int64_t n, const emei_cartpole_params* p,
                            emei_stream_t stream);
 
+/* ---- fused T-step rollout (float32) -------------------------------------------------------------
+ * Replaces the collection loop that calls step(): zoo/util.py:33-93 (reset; while not done: action =
+ * policy | env.action_space.sample(); step; record), batched, with gym's TimeLimit
+ * (register_env.py max_episode_steps) and the per-episode reset done in-kernel.  The state stays in
+ * registers for all `horizon` steps; per step the arithmetic is exactly emei_cartpole_step_f32's. */
+typedef struct emei_rollout_params {
+  int32_t horizon;           /* T: steps per env in this call */
+  int32_t max_episode_steps; /* TimeLimit: truncated when the episode step count reaches it; <= 0: no limit */
+  int32_t auto_reset;        /* 1: an env whose step was done (terminated | truncated) is re-initialised */
+  int32_t random_policy;     /* 1: uniform random actions (action_space.sample()); 0: actions[T,n] supplied */
+  int32_t init_kind;         /* reset sampler: 0 = uniform (cartpole.py:131-132,153-156), 1 = gaussian (mujoco_env.py:137-140) */
+  int32_t init_pi_column;    /* uniform: column that gets +pi (-1 none) */
+  uint64_t seed_reset;       /* Philox key base of the reset sampler: episode k of an env uses seed_reset + k*0xD1B54A32D192ED03 */
+  uint64_t seed_action;      /* Philox key of the random policy: one 32-bit word per (env, t0 + t) */
+  uint64_t env_offset;       /* global id of env 0 (sharding) */
+  uint64_t t0;               /* global step index of the first step of this call (continues the action stream) */
+  double init_low, init_high;              /* uniform range */
+  double init_mean[4], init_sigma[4];      /* gaussian parameters */
+  double action_low, action_high;          /* continuous random policy range */
+} emei_rollout_params;
+
+/*   state_io [n,4] ; episode_step_io int32[n] ; episode_return_io float[n] ; episode_index_io int32[n]  (read+written)
+ *   actions  [horizon,n] in p->action_kind, or NULL when random_policy
+ *   rec_*    optional transition records (all NULL or all set), the reference's dataset keys (zoo/util.py:62-67):
+ *            observations [T,n,4], next_observations [T,n,4], actions [T,n] (p->action_kind element type),
+ *            rewards [T,n], dones [T,n] u8 (terminated | truncated), timeouts [T,n] u8 (truncated)
+ *   stats    nullable double[6], accumulated: {sum of rewards, #terminated, #truncated, #episodes finished,
+ *            sum of finished-episode returns, sum of finished-episode lengths} (-> avg_reward / avg_length
+ *            of zoo/util.py:87-91).  n <= 2^31 - 2^20. */
+int emei_cartpole_rollout_f32(float* state_io, int32_t* episode_step_io, float* episode_return_io,
+                              int32_t* episode_index_io, const void* actions, float* rec_observations,
+                              float* rec_next_observations, void* rec_actions, float* rec_rewards, uint8_t* rec_dones,
+                              uint8_t* rec_timeouts, double* stats, int64_t n, const emei_cartpole_params* p,
+                              const emei_rollout_params* r, emei_stream_t stream);
+
 /* ---- charged ball ----------------------------------------------------------------------------- */
 typedef struct emei_charged_ball_params {
   double gravity_acc, mass_ball, radius, charge, time_step; /* charged_ball.py:13-17 */

@@ -690,3 +690,126 @@ def test_step_host_equals_step(env_id, n):
     else:
         assert torch.equal(sa, sb)
     assert a.read_stats()[1] == b.read_stats()[1]
+
+
+# ================================================================================================
+# fused T-step rollout: zoo/util.py:33-93 batched, TimeLimit + auto-reset in-kernel
+# ================================================================================================
+from oracle import rollout_oracle as RO  # noqa: E402
+
+
+@pytest.mark.parametrize("env_id,kind,cont", (
+    ("CartPoleSwingUp-v0", "swingup", False),
+    ("ContinuousCartPoleSwingUp-v0", "continuous_swingup", True),
+    ("CartPoleBalancing-v0", "balancing", False),
+))
+def test_rollout_teacher_forced_vs_oracle(env_id, kind, cont):
+    """Every recorded transition is checked against the oracle's step from the recorded observation
+    (teacher-forced), the TimeLimit / done / auto-reset bookkeeping against the restated loop, the
+    reset samples against the Philox mirror, and each step bit-for-bit against the step kernel."""
+    n, T, fr = 512, 40, 4
+    max_steps = 3 if kind == "balancing" else 25  # balancing under random pushes falls within a few steps
+    env = E.make(env_id, num_envs=n, dtype=torch.float32, freq_rate=fr)
+    env.reset(seed=3)
+    rng = np.random.default_rng(1)
+    acts = rng.uniform(-1, 1, size=(T, n)).astype(np.float32) if cont else rng.integers(0, 2, size=(T, n)).astype(np.uint8)
+    st0 = env.state.cpu().numpy().copy()
+    if kind != "balancing":  # push a slice near the rail so that terminations happen inside the horizon
+        st0[: n // 4, 0] = np.sign(st0[: n // 4, 0] + 1e-9) * 4.9
+        st0[: n // 4, 1] = np.sign(st0[: n // 4, 0]) * 3.0
+        env.state = st0
+    out = env.rollout(T, actions=acts, record=True, max_episode_steps=max_steps)
+    obs, nxt, ra = (out[k].cpu().numpy() for k in ("observations", "next_observations", "actions"))
+    rew, dones, tmo = (out[k].cpu().numpy() for k in ("rewards", "dones", "timeouts"))
+    assert np.array_equal(ra, acts) and np.array_equal(obs[0], st0)
+    p = O.cartpole_params(kind)
+    seed_reset, _ = RO.rollout_seeds(3)
+    pi_col = 2 if "swingup" in kind else -1
+    ep_step, ep_ret, ep_idx = np.zeros(n, np.int64), np.zeros(n, np.float32), np.zeros(n, np.int64)
+    stepper = E.make(env_id, num_envs=n, dtype=torch.float32, freq_rate=fr)
+    fin, fin_ret, fin_len, n_term = 0, 0.0, 0, 0
+    for t in range(T):
+        ref = O.cartpole_step_f64ref(obs[t].astype(np.float64), O.cartpole_force(acts[t].reshape(-1, 1) if cont else acts[t], cont, p), 0.02, fr, p)
+        assert within32(nxt[t], ref).all()
+        assert within32(rew[t], O.cartpole_reward(kind, ref)[:, 0]).all()
+        near = (np.abs(np.abs(ref[:, 0]) - p.x_threshold) < 1e-4) | (np.abs(np.abs(ref[:, 2]) - p.theta_threshold_radians) < 1e-4)
+        term = O.cartpole_terminal(kind, nxt[t].astype(np.float64), p)[:, 0]  # flags from the engine's own next_obs
+        assert np.array_equal(term[~near], O.cartpole_terminal(kind, ref, p)[:, 0][~near])
+        done, trunc, ep_step, ep_ret = RO.bookkeeping(term, max_steps, ep_step, ep_ret, rew[t])
+        assert np.array_equal(dones[t], done) and np.array_equal(tmo[t], trunc)
+        n_term += int(term.sum())
+        # the step kernel computes the same bits
+        stepper.state = obs[t]
+        o2, r2, d2, _, _ = stepper.step(acts[t])
+        assert np.array_equal(o2.cpu().numpy(), nxt[t]) and np.array_equal(r2.cpu().numpy()[:, 0], rew[t])
+        assert np.array_equal(d2.cpu().numpy()[:, 0], term)
+        # auto-reset: next observation = next_obs, or a fresh Philox reset sample
+        idx = np.nonzero(done)[0]
+        fin += idx.size
+        fin_ret += float(ep_ret[idx].astype(np.float64).sum())
+        fin_len += int(ep_step[idx].sum())
+        ep_idx[idx] += 1
+        expect = nxt[t].copy()
+        if idx.size:
+            expect[idx] = RO.reset_sample_uniform(idx, ep_idx[idx], seed_reset, pi_column=pi_col)
+        ep_step[idx], ep_ret[idx] = 0, 0.0
+        nxt_state = obs[t + 1] if t + 1 < T else env.state.cpu().numpy()
+        assert np.array_equal(nxt_state, expect)
+    assert fin > 0 and tmo.any() and (dones & ~tmo).any()  # both ways of ending an episode were exercised
+    info = env.rollout_info(out["stats"])
+    assert info["total_episode_num"] == fin and info["terminated"] == n_term
+    assert info["truncated"] == int(tmo.sum())
+    assert abs(info["reward_sum"] - float(rew.astype(np.float64).sum())) < 1e-3 * max(1.0, abs(float(rew.sum())))
+    assert abs(info["avg_length"] - fin_len / fin) < 1e-9 and abs(info["avg_reward"] - fin_ret / fin) < 1e-3
+    assert np.array_equal(env._engine.ep_step.cpu().numpy(), ep_step) and np.array_equal(env._engine.ep_index.cpu().numpy(), ep_idx)
+
+
+@pytest.mark.parametrize("env_id,cont", (("CartPoleSwingUp-v0", False), ("ContinuousCartPoleSwingUp-v0", True),
+                                         ("BoundaryInvertedPendulumSwingUp-v0", True)))
+def test_rollout_random_policy_and_split_horizon(env_id, cont):
+    """Built-in random policy = the Philox mirror, bit for bit; one rollout of T steps equals two of T/2
+    (state, counters and the action stream continue); records off = records on."""
+    n, T = 2048, 24
+    a = E.make(env_id, num_envs=n, dtype=torch.float32, freq_rate=1)
+    b = E.make(env_id, num_envs=n, dtype=torch.float32, freq_rate=1)
+    c = E.make(env_id, num_envs=n, dtype=torch.float32, freq_rate=1)
+    for e in (a, b, c):
+        e.reset(seed=21)
+    full = a.rollout(T, record=True, max_episode_steps=10)
+    h1 = b.rollout(T // 2, record=True, max_episode_steps=10)
+    h2 = b.rollout(T // 2, record=True, max_episode_steps=10)
+    c.rollout(T, record=False, max_episode_steps=10)
+    for k in ("observations", "next_observations", "actions", "rewards", "dones", "timeouts"):
+        assert torch.equal(full[k], torch.cat([h1[k], h2[k]], dim=0)), k
+    assert torch.equal(a.state, b.state) and torch.equal(a.state, c.state)
+    assert torch.allclose(full["stats"], h1["stats"] + h2["stats"], rtol=1e-9)
+    _, seed_action = RO.rollout_seeds(21)
+    lo, hi = (float(a.action_space.low[0]), float(a.action_space.high[0])) if cont else (0, 1)
+    ref = RO.random_actions(seed_action, n, 0, T, cont, lo, hi)
+    got = full["actions"].cpu().numpy()
+    assert np.array_equal(got, ref)
+    if not cont:
+        assert 0.45 < got.mean() < 0.55
+    assert full["timeouts"].any()
+
+
+def test_rollout_ip_reset_samples_and_wrap():
+    n, T = 1024, 30
+    env = E.make("BoundaryInvertedPendulumSwingUp-v0", num_envs=n, dtype=torch.float32)
+    env.reset(seed=8)
+    st0 = env.state.cpu().numpy().copy()
+    st0[:, 1] += 50.0  # un-wrapped angles: the recorded observation must be wrapped, the state not
+    env.state = st0
+    out = env.rollout(T, record=True, max_episode_steps=7)
+    obs, nxt, dones = (out[k].cpu().numpy() for k in ("observations", "next_observations", "dones"))
+    assert np.all(np.abs(obs[..., 1]) <= np.pi + 1e-6) and np.all(np.abs(nxt[..., 1]) <= np.pi + 1e-6)
+    seed_reset, _ = RO.rollout_seeds(8)
+    sp = np.full(4, 5e-3)
+    ep_idx = np.zeros(n, np.int64)
+    for t in range(T - 1):
+        idx = np.nonzero(dones[t])[0]
+        ep_idx[idx] += 1
+        if idx.size:
+            ref = RO.reset_sample_gaussian(idx[:16], ep_idx[idx[:16]], seed_reset, np.zeros(4), sp)
+            assert np.allclose(obs[t + 1][idx[:16]], ref, rtol=0, atol=1e-9)
+    assert dones.any()
