@@ -170,6 +170,7 @@ class Workload:
     dtype = "f32"
     scaling = "weak"
     use_graph = True
+    bound = "hbm"  # which roofline bounds the dominant kernel: "hbm" | "issue" (warp-instruction issue)
     alg_bytes = 0  # algorithmic bytes per unit (SURVEY.md 8d / DESIGN.md 5)
     cpu_kind = None  # which oracle routine is the CPU baseline
     cpu_sample = 1 << 20
@@ -429,7 +430,136 @@ class ScoringSweep(Workload):
                 "l2_policy": "inputs larger than L2 (10 GB per sweep)"}
 
 
-WORKLOADS = {w.key: w for w in (IPStep, CartPoleStep, HopperScoring, HalfCheetahScoring, ChargedBall, ScoringSweep)}
+class CartPoleRollout(Workload):
+    """the collection loop (zoo/util.py:33-93) as ONE launch per `horizon` env-steps: state,
+    TimeLimit counter and episode return in registers, in-kernel auto-reset and uniform random policy.  No
+    per-step HBM traffic (24 B per env per launch), so the bound is warp-instruction issue."""
+
+    key, metric, unit = "rollout", "env_steps_per_sec", "env-steps/s"
+    name = "ContinuousCartPoleSwingUp fused rollout, 2^20 envs/GPU x horizon steps per launch, freq_rate=4, in-kernel random policy + TimeLimit(1000) + auto-reset, float32 (SURVEY 8f rank 1)"
+    kernel = "emei::cartpole_rollout_f32_kernel<IP=0, AK=f32, FR=4, RECORD=0>"
+    env_id, n_envs, freq_rate = "ContinuousCartPoleSwingUp-v0", 1 << 20, 4
+    use_graph, bound = False, "issue"
+    record = False
+    alg_bytes = 0.0  # set in setup(): per env-step
+    inst_per_unit = 349.0  # warp-level SASS instructions per env-step incl. divergent in-kernel resets (ncu smsp__inst_executed, profiles/r01_launches_rollout*.csv)
+    cpu_kind = "c2"
+    e2e_max_steps = 5
+
+    def setup(self):
+        import torch
+
+        import emei_b200 as E
+
+        self.T = self.args.horizon
+        self.units = self.n_envs * self.T
+        self.env = E.make(self.env_id, freq_rate=self.freq_rate, real_time_scale=DT, num_envs=self.n_envs,
+                          dtype=torch.float32, device=self.dev, env_offset=self.rank * self.n_envs)
+        self.env.reset(seed=1006)
+        self.stats = self.env.stats
+        # state 16 + 3 counters 12, read and written once per launch; records (if any) per env-step
+        self.alg_bytes = 2 * 28 / self.T + (42 if self.record else 0)
+
+    def step(self, i):
+        self.out = self.env.rollout(self.T, record=self.record)
+
+    def setup_e2e(self):
+        import torch
+
+        rng = np.random.default_rng(1006 + self.rank)
+        self.act_host = [torch.as_tensor(rng.uniform(-1, 1, size=(self.T, self.n_envs)).astype(np.float32)).pin_memory() for _ in range(2)]
+        self.h2d = self.act_host[0].numel() * 4
+        self.d2h = 48
+        self.e2e_api = "env.rollout(horizon, actions=pinned HOST [T,n] float32) -> env.rollout_info(stats) read on the host"
+
+    def step_e2e(self, i):
+        out = self.env.rollout(self.T, actions=self.act_host[i % 2])
+        self.info = self.env.rollout_info(out["stats"])
+
+    def config(self):
+        return {"envs_per_gpu": self.n_envs, "horizon": self.T, "freq_rate": self.freq_rate, "max_episode_steps": 1000,
+                "records": self.record,
+                "l2_policy": "no reuse to defeat: every env's state is read once and written once per launch"
+                             + (f"; records are {self.units * 42 / 1e6:.0f} MB of fresh writes per launch" if self.record else "")}
+
+
+class CartPoleRolloutRecord(CartPoleRollout):
+    """Same launch, additionally writing every transition in the reference's dataset layout (zoo/util.py:62-67):
+    observations/next_observations [T,n,4], actions/rewards [T,n], dones/timeouts u8[T,n] = 42 B per env-step."""
+
+    key = "rollout_rec"
+    name = CartPoleRollout.name.replace("fused rollout", "fused rollout + transition records (dataset layout)")
+    kernel = "emei::cartpole_rollout_f32_kernel<IP=0, AK=f32, FR=4, RECORD=1>"
+    record = True
+    inst_per_unit = 382.0  # t_issue = 0.34 ms > t_hbm = 0.22 ms (42 B/env-step) at 2^25 env-steps per launch: still issue-bound
+
+    def setup(self):
+        if not self.args.horizon_set:
+            self.args.horizon = 32
+        super().setup()
+
+    def setup_e2e(self):
+        self.h2d = self.d2h = 0
+        self.e2e_api = None
+
+
+class ChargedBallRollout(Workload):
+    """C4 as BASELINE words it ("rollouts, 64M envs x 200 steps"): ONE launch advances every env of the shard by
+    `horizon` steps with the state in registers (emei_charged_ball_rollout_f32), in-kernel Bernoulli(1/2) policy,
+    TimeLimit(500) + auto-reset.  HBM is touched once per env per launch, so the bound is warp-instruction issue."""
+
+    key, metric, unit = "c4_rollout", "env_steps_per_sec", "env-steps/s"
+    name = "ChargedBallCentering fused rollouts, 2^26 envs total sharded over the ranks x 200 steps per launch, freq_rate=1, float32 (BASELINE configs[3])"
+    kernel = "emei::rollout_f32_kernel<ChargedBallDyn<u8>, RECORD=0>"
+    scaling, use_graph, bound = "strong", False, "issue"
+    total = 1 << 26
+    inst_per_unit = 166.0  # warp-level SASS instructions per env-step, all three divergent paths issued (ncu smsp__inst_executed, profiles/r01_launches_c4_rollout.csv)
+    cpu_kind, cpu_sample = "c4", 1 << 20
+    e2e_max_steps = 5
+
+    def setup(self):
+        import torch
+
+        import emei_b200 as E
+        from emei_b200.dist import shard_range
+
+        if self.args.total_log2:
+            self.total = 1 << self.args.total_log2
+        self.T = self.args.horizon if self.args.horizon_set else 200
+        b, e = shard_range(self.total, self.rank, self.world)
+        self.n = e - b
+        self.units = self.n * self.T
+        self.env = E.make("ChargedBallCentering-v0", num_envs=self.n, dtype=torch.float32, device=self.dev, env_offset=b)
+        self.env.reset(seed=1004)
+        self.stats = self.env.stats
+        self.alg_bytes = 2 * (25 + 12) / self.T  # state 25 + 3 episode counters 12, read + written once per launch
+
+    def step(self, i):
+        self.out = self.env.rollout(self.T)
+
+    def setup_e2e(self):
+        import torch
+
+        # teacher-forced policy from the host: uint8 [T, n] actions in pinned memory, statistics read back
+        self.Te = min(self.T, 25)
+        g = torch.Generator()
+        g.manual_seed(1004 + self.rank)
+        self.act_host = [torch.randint(0, 2, (self.Te, self.n), dtype=torch.uint8, generator=g).pin_memory() for _ in range(2)]
+        self.h2d, self.d2h = self.Te * self.n, 48
+        self.e2e_units = self.n * self.Te
+        self.e2e_api = f"env.rollout({self.Te}, actions=pinned HOST uint8[{self.Te}, n]) -> env.rollout_info(stats) read on the host"
+
+    def step_e2e(self, i):
+        out = self.env.rollout(self.Te, actions=self.act_host[i % 2])
+        self.info = self.env.rollout_info(out["stats"])
+
+    def config(self):
+        return {"envs_total": self.total, "envs_per_gpu": self.n, "horizon": self.T, "freq_rate": 1, "max_episode_steps": 500,
+                "l2_policy": f"no reuse to defeat: {self.n * 37 / 1e6:.0f} MB of state read once and written once per launch"}
+
+
+WORKLOADS = {w.key: w for w in (IPStep, CartPoleStep, HopperScoring, HalfCheetahScoring, ChargedBall, ScoringSweep,
+                                CartPoleRollout, CartPoleRolloutRecord, ChargedBallRollout)}
 
 
 # ==================================================================================================
@@ -598,6 +728,7 @@ def run_ours(args):
     wl.setup_e2e()
     if wl.e2e_api is not None:
         e2e_steps = max(3, min(K, args.e2e_steps))
+        e2e_steps = min(e2e_steps, getattr(wl, "e2e_max_steps", e2e_steps))
         for i in range(2):
             wl.step_e2e(i)
         torch.cuda.synchronize()
@@ -614,8 +745,9 @@ def run_ours(args):
         te = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e_units = float(units.item()) * getattr(wl, "e2e_units", wl.units) / wl.units
         e2e = {
-            "value": float(units.item()) * e2e_steps / (float(te.item()) * 1e-3), "unit": wl.unit,
+            "value": e2e_units * e2e_steps / (float(te.item()) * 1e-3), "unit": wl.unit,
             "h2d_bytes_per_step": wl.h2d, "d2h_bytes_per_step": wl.d2h, "steps": e2e_steps, "api": wl.e2e_api,
         }
     clocks = sampler.finish() if rank == 0 else None
@@ -634,7 +766,17 @@ def run_ours(args):
                 + (" (timed region / launches, inter-launch gaps included)" if wl.use_graph else ""),
     }
     ipu = getattr(wl, "inst_per_unit", None)
-    if ipu:  # the second roofline of the north star: warp-instruction issue (148 SMs x 4 schedulers x clock)
+    if wl.bound == "issue":  # no per-unit HBM traffic to speak of: the roofline is warp-instruction issue
+        issue_peak = 148 * 4 * sm_mhz * 1e6
+        ach = ipu * wl.units / 32.0 / (kern_ms * 1e-3)
+        roofline = {
+            "bound": "issue", "achieved": ach / 1e9, "peak": issue_peak / 1e9, "unit": "G warp-inst/s", "frac": ach / issue_peak,
+            "traffic": None, "peak_source": f"148 SMs x 4 schedulers x {sm_mhz:.0f} MHz (MEASURED_PEAKS.json sm_max_mhz), 1 warp instruction per scheduler per clock",
+            "warp_inst_per_unit": ipu, "kernel": wl.kernel, "kernel_ms_per_launch": kern_ms,
+            "hbm": {"algorithmic_bytes_per_unit": wl.alg_bytes, "achieved_gbs": achieved, "frac_of_hbm_peak": achieved / peak},
+            "note": "duration = CUDA-event time per launch; instruction count per env-step from ncu smsp__inst_executed (profiles/)",
+        }
+    elif ipu:  # the second roofline of the north star: warp-instruction issue (148 SMs x 4 schedulers x clock)
         issue_peak = 148 * 4 * sm_mhz * 1e6
         t_math = ipu * wl.units / 32.0 / issue_peak
         t_hbm = wl.alg_bytes * wl.units / (peak * 1e9)
@@ -679,7 +821,11 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=30)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--total-log2", type=int, default=0, help="c4 only: log2 of the total env count (default 26)")
+    ap.add_argument("--horizon", type=int, default=None, help="rollout workloads: env-steps per launch (default 100; 32 with records)")
     args = ap.parse_args()
+    args.horizon_set = args.horizon is not None
+    if args.horizon is None:
+        args.horizon = 100
     if args.steps is None:
         args.steps = 2000 if WORKLOADS[args.workload].use_graph else 20
         if args.impl == "reference":

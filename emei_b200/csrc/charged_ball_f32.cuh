@@ -37,12 +37,113 @@ inline ChargedBallF32Consts make_cb_f32_consts(const emei_charged_ball_params& p
   return k;
 }
 
-// charged_ball.py:30-36 (cold path: only evaluated when a ball lands)
-__device__ __noinline__ float cb_get_angle_f32(float x, float y, float r, float eps) {
-  const float scale = sqrtf(x * x + y * y);
-  const float a = asinf(x / (scale * r + eps));
+__device__ __forceinline__ float sqrt_fast(float x) {  // sqrt.approx: max relative error 2^-23
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
+// charged_ball.py:30-36, evaluated only when a ball lands (2 % of env-steps, but 43 % of warp-steps in a
+// rollout, so its length matters: MUFU sqrt / reciprocal instead of the IEEE sequences, and the `% 2 pi` of an
+// angle that is already in [-pi/2, 3pi/2] as one select -- the same bits as fmodf there).  The MUFU results
+// are within 1 ulp each, so the asin argument may exceed 1 by an ulp or two where the IEEE quotient cannot:
+// clamped (NaN stays NaN).
+__device__ __forceinline__ float cb_get_angle_f32(float x, float y, float r, float eps) {
+  const float scale = sqrt_fast(fmaf(x, x, y * y));
+  float arg = x * f32::rcp_fast(fmaf(scale, r, eps));
+  arg = fabsf(arg) > 1.0f ? copysignf(1.0f, arg) : arg;
+  const float a = asinf(arg);
   const float angle = (y > 0.f) ? a : (3.14159265358979323846f - a);
-  return py_mod(angle, 6.28318530717958647692f);
+  return angle < 0.f ? angle + 6.28318530717958647692f : angle + 0.0f;  // python `%`: result in [0, 2 pi), +0
+}
+
+// sin/cos of the circle angle: lean path for |theta| <= 1e5, libm (Payne-Hanek) beyond / NaN
+__device__ __forceinline__ void cb_sincos(float theta, float* s, float* c) {
+  if (fabsf(theta) <= f32::kSinCosFastMax)
+    f32::sincos_core(theta, s, c);
+  else
+    sincosf(theta, s, c);
+}
+
+// one env's registers.  Invariant kept by cb_env_step: while `on`, (s, c) = sin/cos(theta) -- the value computed
+// for circle_to_free at the end of a sub-step is the one the next sub-step's dynamics needs (same function of
+// the same float32 theta, so carrying it changes no bit).  Callers that load theta from memory establish the
+// invariant with cb_prepare().
+struct CBRegs {
+  bool on;
+  float theta, omega, s, c;
+  float4 f;  // x, y, vx, vy
+};
+
+__device__ __forceinline__ void cb_prepare(CBRegs& e) {
+  e.s = e.c = 0.f;
+  if (e.on) cb_sincos(e.theta, &e.s, &e.c);
+}
+
+template <int AK>
+__device__ __forceinline__ float cb_field(float a, const ChargedBallF32Consts& k) {
+  if constexpr (AK <= EMEI_ACTION_DISCRETE_I64)
+    return a == 1.0f ? k.charge : -k.charge;  // charged_ball.py:155-156
+  else
+    return k.charge * a;  // :169-170
+}
+
+// freq_rate x update_state(_get_update_info(E)) on one env's registers; returns the reward (:158-160).
+// Shared by the step kernel and the fused rollout kernel (rollout_f32.cuh): same bits.
+//
+// In a rollout nearly every warp holds balls on the ring, balls in flight AND a ball that lands in this very
+// step (5 % of env-steps, 85 % of warp-steps), so a warp issues all three paths: they are kept short and share
+// ONE sincos site (after the branches) instead of one per path.
+__device__ __forceinline__ float cb_env_step(CBRegs& e, float E, const ChargedBallF32Consts& k) {
+  bool on = e.on;
+  float theta = e.theta, omega = e.omega, s = e.s, c = e.c;
+  float4 f = e.f;
+  for (int sub = 0; sub < k.freq_rate; ++sub) {
+    bool on_ring = on;  // took the ring path: (x, y, vx, vy) follow from the new (theta, omega)
+    if (on) {
+      // _get_update_info :72-78 + update_state :56-61
+      const float theta_acc = fmaf(s, k.mg, c * E) * k.inv_mr;
+      const bool flag = fmaf(s, E, k.m_r * (omega * omega)) < c * k.mg;  // evaluated on the pre-update state
+      theta = fmaf(omega, k.h, theta);
+      omega = fmaf(theta_acc, k.h, omega);
+      if (flag) on = false;
+    } else {
+      // _get_update_info :79-82 + update_state :62-66 + free_to_circle :44-52
+      const float acc_x = E * k.inv_m;
+      const float nx = fmaf(f.z, k.h, f.x), ny = fmaf(f.w, k.h, f.y);
+      f.z = fmaf(acc_x, k.h, f.z);
+      f.w = fmaf(-k.g, k.h, f.w);
+      f.x = nx;
+      f.y = ny;
+      if (fmaf(f.x, f.x, f.y * f.y) > k.land_thr) {
+        on = true;
+        theta = cb_get_angle_f32(f.x, f.y, k.r, k.eps);
+        // _angle_greater(_get_angle(vx, vy), theta) (:38-42,48-51) asks whether the velocity direction is ahead
+        // of the position direction on the circle of angles, i.e. sin(v_angle - theta) > 0, i.e. the sign of
+        // the cross product vx*y - vy*x: same answer as comparing the two angles (wrap rule included) except
+        // on the measure-zero set where they coincide or oppose exactly, without a second asin.
+        const bool greater = fmaf(f.z, f.y, -(f.w * f.x)) > 0.f;
+        const float speed = sqrt_fast(fmaf(f.z, f.z, f.w * f.w)) * k.inv_r;
+        omega = greater ? speed : -speed;
+      }
+    }
+    if (on_ring || on) {  // the ONE sincos site: ring lanes (circle_to_free :25-28) and lanes that just landed
+      cb_sincos(theta, &s, &c);
+      if (on_ring) {
+        f.x = s * k.r;
+        f.y = c * k.r;
+        f.z = omega * f.y;
+        f.w = -omega * f.x;
+      }
+    }
+  }
+  e.on = on;
+  e.theta = theta;
+  e.omega = omega;
+  e.s = s;
+  e.c = c;
+  e.f = f;
+  return fmaf(-sqrt_fast(fmaf(f.x, f.x, f.y * f.y)), k.inv_r, 1.0f);  // charged_ball.py:158-160
 }
 
 template <int AK>
@@ -59,54 +160,17 @@ __global__ void __launch_bounds__(kBlock, 8)
     // all loads first
     const uint8_t on_u8 = on_circle[i];
     const float2 c2 = circle[i];
-    float4 f = free_state[i];  // x, y, vx, vy
+    CBRegs e;
+    e.f = free_state[i];
     const float a = load_action_f32<AK>(action, i);
-    bool on = on_u8 != 0;
-    float theta = c2.x, omega = c2.y;
-    float E;
-    if constexpr (AK <= EMEI_ACTION_DISCRETE_I64)
-      E = a == 1.0f ? k.charge : -k.charge;  // charged_ball.py:155-156
-    else
-      E = k.charge * a;  // :169-170
-    const bool fast_trig = fabsf(theta) <= f32::kSinCosFastMax;  // NaN / huge angles -> libm
-    for (int sub = 0; sub < k.freq_rate; ++sub) {
-      if (on) {
-        // _get_update_info :72-78 + update_state :56-61 + circle_to_free :25-28
-        float s, c;
-        if (fast_trig) f32::sincos_core(theta, &s, &c); else sincosf(theta, &s, &c);
-        const float theta_acc = fmaf(s, k.mg, c * E) * k.inv_mr;
-        const bool flag = fmaf(s, E, k.m_r * (omega * omega)) < c * k.mg;  // evaluated on the pre-update state
-        theta = fmaf(omega, k.h, theta);
-        omega = fmaf(theta_acc, k.h, omega);
-        float sn, cn;
-        if (fast_trig && fabsf(theta) <= f32::kSinCosSaneMax) f32::sincos_core(theta, &sn, &cn); else sincosf(theta, &sn, &cn);
-        f.x = sn * k.r;
-        f.y = cn * k.r;
-        f.z = omega * f.y;
-        f.w = -omega * f.x;
-        if (flag) on = false;
-      } else {
-        // _get_update_info :79-82 + update_state :62-66 + free_to_circle :44-52
-        const float acc_x = E * k.inv_m;
-        const float nx = fmaf(f.z, k.h, f.x), ny = fmaf(f.w, k.h, f.y);
-        f.z = fmaf(acc_x, k.h, f.z);
-        f.w = fmaf(-k.g, k.h, f.w);
-        f.x = nx;
-        f.y = ny;
-        if (fmaf(f.x, f.x, f.y * f.y) > k.land_thr) {
-          on = true;
-          theta = cb_get_angle_f32(f.x, f.y, k.r, k.eps);
-          const float v_angle = cb_get_angle_f32(f.z, f.w, k.r, k.eps);
-          const bool greater = (fabsf(v_angle - theta) < 3.14159265358979323846f) ? (v_angle > theta) : (v_angle < theta);  // :38-42
-          const float speed = sqrtf(fmaf(f.z, f.z, f.w * f.w)) * k.inv_r;
-          omega = greater ? speed : -speed;
-        }
-      }
-    }
-    on_circle[i] = on ? 1 : 0;
-    circle[i] = make_float2(theta, omega);
-    free_state[i] = f;
-    const float rew = 1.0f - sqrtf(fmaf(f.x, f.x, f.y * f.y)) * k.inv_r;  // charged_ball.py:158-160
+    e.on = on_u8 != 0;
+    e.theta = c2.x;
+    e.omega = c2.y;
+    cb_prepare(e);
+    const float rew = cb_env_step(e, cb_field<AK>(a, k), k);
+    on_circle[i] = e.on ? 1 : 0;
+    circle[i] = make_float2(e.theta, e.omega);
+    free_state[i] = e.f;
     reward[i] = rew;
     done[i] = 0;  // charged_ball.py:110-111
     r_acc += rew;

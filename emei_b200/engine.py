@@ -62,7 +62,72 @@ class StepOutputs:
         self.done = [torch.empty((n, 1), dtype=torch.uint8, device=device) for _ in range(2)]
 
 
-class CartPoleEngine:
+class RolloutMixin:
+    """Episode bookkeeping buffers + the call of a fused T-step rollout entry point (emei_*_rollout_f32)."""
+
+    ep_step = ep_return = ep_index = None
+    t_global = 0
+
+    def _alloc_episode(self):
+        if self.ep_step is None:
+            dev = self.env.device
+            self.ep_step = torch.zeros(self.n, dtype=torch.int32, device=dev)
+            self.ep_return = torch.zeros(self.n, dtype=torch.float32, device=dev)
+            self.ep_index = torch.zeros(self.n, dtype=torch.int32, device=dev)
+            self.t_global = 0
+
+    def new_episodes(self, reseed: bool):
+        """called when the env's state is (re)set from outside: every env starts a fresh episode."""
+        if self.ep_step is not None:
+            self.ep_step.zero_()
+            self.ep_return.zero_()
+            if reseed:
+                self.ep_index.zero_()
+                self.t_global = 0
+
+    def _rollout(self, entry: str, state_ptrs, rp: _lib.RolloutParams, actions, record: bool, rollout_stats: torch.Tensor):
+        env = self.env
+        if env.dtype != torch.float32:
+            raise NotImplementedError("the fused rollout kernel is float32 (use step() for the float64 reference-exact mode)")
+        self._alloc_episode()
+        T, n, dev = int(rp.horizon), self.n, env.device
+        rp.t0 = self.t_global
+        rec = {}
+        if actions is not None:
+            if tuple(actions.shape[:2]) != (T, n) and tuple(actions.shape) != (T, n):
+                raise ValueError(f"actions must be [horizon={T}, num_envs={n}], got {tuple(actions.shape)}")
+            actions = actions.reshape(T, n).contiguous()
+            self.params.action_kind = _ACTION_KIND[actions.dtype]
+            act_dtype = actions.dtype
+        else:
+            cont = len(env.action_space.shape) > 0
+            act_dtype = torch.float32 if cont else torch.uint8
+            self.params.action_kind = _ACTION_KIND[act_dtype]
+        ptrs = [None] * 6
+        if record:
+            rec = dict(
+                observations=torch.empty((T, n, 4), dtype=torch.float32, device=dev),
+                next_observations=torch.empty((T, n, 4), dtype=torch.float32, device=dev),
+                actions=torch.empty((T, n), dtype=act_dtype, device=dev),
+                rewards=torch.empty((T, n), dtype=torch.float32, device=dev),
+                dones=torch.empty((T, n), dtype=torch.uint8, device=dev),
+                timeouts=torch.empty((T, n), dtype=torch.uint8, device=dev),
+            )
+            ptrs = [rec[k].data_ptr() for k in ("observations", "next_observations", "actions", "rewards", "dones", "timeouts")]
+        with torch.cuda.device(dev):
+            _lib.call(
+                entry, *state_ptrs, self.ep_step.data_ptr(), self.ep_return.data_ptr(), self.ep_index.data_ptr(),
+                actions.data_ptr() if actions is not None else None, *ptrs,
+                rollout_stats.data_ptr(), n, ctypes.byref(self.params), ctypes.byref(rp), env._stream(),
+            )
+        self.t_global += T
+        if record:
+            rec["dones"] = rec["dones"].view(torch.bool)
+            rec["timeouts"] = rec["timeouts"].view(torch.bool)
+        return rec
+
+
+class CartPoleEngine(RolloutMixin):
     """cart-pole family + analytic inverted pendulum (emei_cartpole_step_*)."""
 
     def __init__(self, env, params: _lib.CartPoleParams, separate_obs: bool):
@@ -142,65 +207,10 @@ class CartPoleEngine:
         self._cur = 1 - self._cur
 
     # ---- fused T-step rollout (emei_cartpole_rollout_f32) ----------------------------------------
-    def _alloc_episode(self):
-        if getattr(self, "ep_step", None) is None:
-            dev = self.env.device
-            self.ep_step = torch.zeros(self.n, dtype=torch.int32, device=dev)
-            self.ep_return = torch.zeros(self.n, dtype=torch.float32, device=dev)
-            self.ep_index = torch.zeros(self.n, dtype=torch.int32, device=dev)
-            self.t_global = 0
-
-    def new_episodes(self, reseed: bool):
-        """called when the env's state is (re)set from outside: every env starts a fresh episode."""
-        if getattr(self, "ep_step", None) is not None:
-            self.ep_step.zero_()
-            self.ep_return.zero_()
-            if reseed:
-                self.ep_index.zero_()
-                self.t_global = 0
-
     def rollout(self, rp: _lib.RolloutParams, actions, record: bool, rollout_stats: torch.Tensor):
-        env = self.env
-        if env.dtype != torch.float32:
-            raise NotImplementedError("the fused rollout kernel is float32 (use step() for the float64 reference-exact mode)")
         self._alloc()
-        self._alloc_episode()
         state = self._bufs[self._cur]
-        T, n, dev = int(rp.horizon), self.n, env.device
-        rp.t0 = self.t_global
-        rec = {}
-        if actions is not None:
-            if tuple(actions.shape[:2]) != (T, n) and tuple(actions.shape) != (T, n):
-                raise ValueError(f"actions must be [horizon={T}, num_envs={n}], got {tuple(actions.shape)}")
-            actions = actions.reshape(T, n).contiguous()
-            self.params.action_kind = _ACTION_KIND[actions.dtype]
-            act_dtype = actions.dtype
-        else:
-            cont = len(env.action_space.shape) > 0
-            act_dtype = torch.float32 if cont else torch.uint8
-            self.params.action_kind = _ACTION_KIND[act_dtype]
-        ptrs = [None] * 6
-        if record:
-            rec = dict(
-                observations=torch.empty((T, n, 4), dtype=torch.float32, device=dev),
-                next_observations=torch.empty((T, n, 4), dtype=torch.float32, device=dev),
-                actions=torch.empty((T, n), dtype=act_dtype, device=dev),
-                rewards=torch.empty((T, n), dtype=torch.float32, device=dev),
-                dones=torch.empty((T, n), dtype=torch.uint8, device=dev),
-                timeouts=torch.empty((T, n), dtype=torch.uint8, device=dev),
-            )
-            ptrs = [rec[k].data_ptr() for k in ("observations", "next_observations", "actions", "rewards", "dones", "timeouts")]
-        with torch.cuda.device(dev):
-            _lib.call(
-                "emei_cartpole_rollout_f32", state.data_ptr(), self.ep_step.data_ptr(), self.ep_return.data_ptr(),
-                self.ep_index.data_ptr(), actions.data_ptr() if actions is not None else None, *ptrs,
-                rollout_stats.data_ptr(), n, ctypes.byref(self.params), ctypes.byref(rp), env._stream(),
-            )
-        self.t_global += T
-        if record:
-            rec["dones"] = rec["dones"].view(torch.bool)
-            rec["timeouts"] = rec["timeouts"].view(torch.bool)
-        return rec
+        return self._rollout("emei_cartpole_rollout_f32", [state.data_ptr()], rp, actions, record, rollout_stats)
 
     def next_obs_stateless(self, obs: torch.Tensor, action: torch.Tensor):
         """get_batch_next_obs: one dynamics step from caller-supplied observations (any batch size);
@@ -235,8 +245,12 @@ class CartPoleEngine:
         self.has_state = True
 
 
-class ChargedBallEngine:
+class ChargedBallEngine(RolloutMixin):
     """charged ball (emei_charged_ball_step_*): three state arrays updated in place."""
+
+    def rollout(self, rp: _lib.RolloutParams, actions, record: bool, rollout_stats: torch.Tensor):
+        ptrs = [self.on_circle.data_ptr(), self.circle.data_ptr(), self.free.data_ptr()]
+        return self._rollout("emei_charged_ball_rollout_f32", ptrs, rp, actions, record, rollout_stats)
 
     def __init__(self, env, params: _lib.ChargedBallParams):
         self.env = env
@@ -262,6 +276,7 @@ class ChargedBallEngine:
         self.circle.copy_(env._to_device(circle, env.dtype)[0].reshape(self.n, 2))
         self.free.copy_(env._to_device(free, env.dtype)[0].reshape(self.n, 4))
         self.has_state = True
+        self.new_episodes(reseed=False)
 
     def sample_initial(self, seed: int, env_offset: int):
         self._alloc()

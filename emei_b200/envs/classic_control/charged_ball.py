@@ -61,7 +61,14 @@ class BaseChargedBallEnv(BaseControlEnv):
     def reset(self, *, seed=None, options=None):
         self._reseed(seed)
         self._engine.sample_initial(self._next_sample_seed(), self.env_offset)  # charged_ball.py:84-94
+        self._engine.new_episodes(reseed=True)
         return self._engine.free.clone(), {}
+
+    def _rollout_params(self) -> _lib.RolloutParams:
+        rp = _lib.RolloutParams()
+        rp.init_kind, rp.init_pi_column = 2, -1  # in-kernel reset = charged_ball.py:84-94
+        rp.action_low, rp.action_high = -1.0, 1.0
+        return rp
 
     def get_batch_init_state(self, batch_size):
         tmp = type(self)(freq_rate=self.freq_rate, num_envs=batch_size, device=self.device, dtype=self.dtype,

@@ -121,7 +121,7 @@ typedef struct emei_rollout_params {
   int32_t init_kind;         /* reset sampler: 0 = uniform (cartpole.py:131-132,153-156), 1 = gaussian (mujoco_env.py:137-140) */
   int32_t init_pi_column;    /* uniform: column that gets +pi (-1 none) */
   uint64_t seed_reset;       /* Philox key base of the reset sampler: episode k of an env uses seed_reset + k*0xD1B54A32D192ED03 */
-  uint64_t seed_action;      /* Philox key of the random policy: one 32-bit word per (env, t0 + t) */
+  uint64_t seed_action;      /* Philox key of the random policy stream of each env: 1 bit (Discrete) / one 32-bit word (Box) per step t0 + t */
   uint64_t env_offset;       /* global id of env 0 (sharding) */
   uint64_t t0;               /* global step index of the first step of this call (continues the action stream) */
   double init_low, init_high;              /* uniform range */
@@ -160,6 +160,17 @@ int emei_charged_ball_step_f32(uint8_t* on_circle, float* circle, float* free_st
 int emei_charged_ball_step_f64(uint8_t* on_circle, double* circle, double* free_state, const void* action,
                                double* reward, uint8_t* done, double* stats, int64_t n,
                                const emei_charged_ball_params* p, emei_stream_t stream);
+
+/* Fused T-step charged-ball rollout (float32): as emei_cartpole_rollout_f32 (zoo/util.py:33-93 batched) with the
+ * three state arrays of emei_charged_ball_step_f32 kept in registers for all `horizon` steps; per step the arithmetic
+ * is exactly emei_charged_ball_step_f32's.  terminated is always 0 (charged_ball.py:110-111), so episodes end by the
+ * TimeLimit only (register_env.py:34-43: 500 / 1000 steps).  The in-kernel reset is charged_ball.py:84-94
+ * (r->init_kind / init_* are ignored).  Records: observations / next_observations are the `free` array. */
+int emei_charged_ball_rollout_f32(uint8_t* on_circle_io, float* circle_io, float* free_state_io, int32_t* episode_step_io,
+                                  float* episode_return_io, int32_t* episode_index_io, const void* actions,
+                                  float* rec_observations, float* rec_next_observations, void* rec_actions,
+                                  float* rec_rewards, uint8_t* rec_dones, uint8_t* rec_timeouts, double* stats, int64_t n,
+                                  const emei_charged_ball_params* p, const emei_rollout_params* r, emei_stream_t stream);
 
 /* ---- model-based scoring: get_batch_reward + get_batch_terminal fused ------------------------- */
 typedef struct emei_scoring_params {

@@ -49,19 +49,34 @@ def reset_sample_gaussian(env_ids, ep_index, seed_reset, mean, sigma):
     return out
 
 
+def reset_sample_charged_ball(env_ids, ep_index, seed_reset, radius=1.0):
+    """(on_circle u8[m], circle f32[m,2], free f32[m,4]) of charged_ball.py:84-94 for the in-rollout episodes.
+    circle is bit-exact (float32 casts of exact float64 arithmetic); free goes through float32 sin/cos (<= 1 ulp
+    from the device's sincosf)."""
+    env_ids = np.asarray(env_ids, dtype=np.uint64)
+    m = env_ids.shape[0]
+    on, circle, free = np.ones(m, np.uint8), np.empty((m, 2), np.float32), np.empty((m, 4), np.float32)
+    for j in range(m):
+        s = (seed_reset + int(ep_index[j]) * RESET_STRIDE) & MASK64
+        _, c, f = P.init_charged_ball(1, radius, s, env_offset=int(env_ids[j]), dtype=np.float32)
+        circle[j], free[j] = c[0], f[0]
+    return on, circle, free
+
+
 def random_actions(seed_action, n, t0, horizon, continuous, low=-1.0, high=1.0, env_offset=0):
     """[horizon, n] actions of the engine's uniform random policy (env.action_space.sample() of zoo/util.py:57)."""
     env = np.arange(n, dtype=np.uint64) + np.uint64(env_offset)
     out = np.empty((horizon, n), dtype=np.float32 if continuous else np.uint8)
     for t in range(horizon):
         tg = t0 + t
-        w = P.philox4x32_10(seed_action, env, np.full(n, tg >> 2), PURPOSE_ROLLOUT_ACTION)[tg & 3]
-        if continuous:
+        if continuous:  # one 32-bit word per step: block tg // 4, word tg % 4, top 24 bits
+            w = P.philox4x32_10(seed_action, env, np.full(n, tg >> 2), PURPOSE_ROLLOUT_ACTION)[tg & 3]
             u = (w >> np.uint32(8)).astype(np.float32) * np.float32(1.0 / 16777216.0)
             # float32 fma(high-low, u, low): the product is exact in float64, one rounding at the end
             out[t] = (np.float64(np.float32(high) - np.float32(low)) * u.astype(np.float64) + np.float64(np.float32(low))).astype(np.float32)
-        else:
-            out[t] = (w & np.uint32(1)).astype(np.uint8)
+        else:  # one bit per step: block tg // 128, word (tg // 32) % 4, bit tg % 32
+            w = P.philox4x32_10(seed_action, env, np.full(n, tg >> 7), PURPOSE_ROLLOUT_ACTION)[(tg >> 5) & 3]
+            out[t] = ((w >> np.uint32(tg & 31)) & np.uint32(1)).astype(np.uint8)
     return out
 
 

@@ -396,6 +396,43 @@ def test_charged_ball_f32_teacher_forced(golden, tag):
     assert okc[agree & on0 & r_on].all()
 
 
+def test_charged_ball_f32_landing_vs_oracle():
+    """free_to_circle (charged_ball.py:44-52) in float32: balls in free flight just inside the ring, moving
+    outwards, land in this step.  Where asin is well conditioned (|x|/r < 0.9 for position and velocity) the
+    re-derived (theta, omega) must meet the float32 tolerance; everywhere the landing flag must agree."""
+    n = 8192
+    rng = np.random.default_rng(77)
+    ang = rng.uniform(0, 2 * np.pi, n)
+    rad = rng.uniform(0.97, 0.9999, n)
+    pos = np.stack([rad * np.sin(ang), rad * np.cos(ang)], axis=1)
+    vdir = ang + rng.uniform(-1.2, 1.2, n)  # outward-ish
+    speed = rng.uniform(2.5, 6.0, n)
+    vel = np.stack([speed * np.sin(vdir), speed * np.cos(vdir)], axis=1)
+    fr32 = np.concatenate([pos, vel], axis=1).astype(np.float32)
+    on0 = np.zeros(n, dtype=bool)
+    ci32 = np.zeros((n, 2), dtype=np.float32)
+    act = rng.integers(0, 2, size=n)
+    p = O.ChargedBallParams()
+    r_on, r_ci, r_fr = O.charged_ball_step(on0, ci32.astype(np.float64), fr32.astype(np.float64), O.charged_ball_force(act, False, p), 1, p)
+    env = CB.ChargedBallCenteringEnv(num_envs=n, dtype=torch.float32)
+    env.state = dict(on_circle=on0.astype(np.uint8), circle_state=ci32, free_state=fr32)
+    env.step(act)
+    st = env.state
+    got_on = st["on_circle"].cpu().numpy().astype(bool)
+    r2 = (r_fr[:, 0] ** 2 + r_fr[:, 1] ** 2)
+    near = np.abs(r2 - (1.0 + 0.001)) < 1e-5
+    assert np.array_equal(got_on[~near], r_on[~near]) and 0.3 < r_on.mean() < 1.0
+    assert within32(st["free_state"].cpu().numpy(), r_fr, 2.0).all()
+    vn = np.sqrt(r_fr[:, 2] ** 2 + r_fr[:, 3] ** 2)
+    well = r_on & got_on & (np.abs(r_fr[:, 0]) / np.sqrt(r2) < 0.9) & (np.abs(r_fr[:, 2]) / vn < 0.9)
+    got_ci = st["circle_state"].cpu().numpy().astype(np.float64)
+    assert well.sum() > 1000
+    assert within32(got_ci[well, 0], r_ci[well, 0], 4.0).all()
+    same_sign = np.sign(got_ci[well, 1]) == np.sign(r_ci[well, 1])
+    assert same_sign.mean() > 0.999
+    assert within32(np.abs(got_ci[well, 1]), np.abs(r_ci[well, 1]), 4.0).all()
+
+
 def test_charged_ball_reset_and_rollout_stats():
     env = CB.ChargedBallCenteringEnv(num_envs=2048, dtype=torch.float64)
     obs, _ = env.reset(seed=9)
@@ -764,8 +801,15 @@ def test_rollout_teacher_forced_vs_oracle(env_id, kind, cont):
     assert np.array_equal(env._engine.ep_step.cpu().numpy(), ep_step) and np.array_equal(env._engine.ep_index.cpu().numpy(), ep_idx)
 
 
+def _same_state(a, b):
+    if isinstance(a, dict):
+        return all(torch.equal(a[k], b[k]) for k in a)
+    return torch.equal(a, b)
+
+
 @pytest.mark.parametrize("env_id,cont", (("CartPoleSwingUp-v0", False), ("ContinuousCartPoleSwingUp-v0", True),
-                                         ("BoundaryInvertedPendulumSwingUp-v0", True)))
+                                         ("BoundaryInvertedPendulumSwingUp-v0", True), ("ChargedBallCentering-v0", False),
+                                         ("ContinuousChargedBallCentering-v0", True)))
 def test_rollout_random_policy_and_split_horizon(env_id, cont):
     """Built-in random policy = the Philox mirror, bit for bit; one rollout of T steps equals two of T/2
     (state, counters and the action stream continue); records off = records on."""
@@ -781,7 +825,7 @@ def test_rollout_random_policy_and_split_horizon(env_id, cont):
     c.rollout(T, record=False, max_episode_steps=10)
     for k in ("observations", "next_observations", "actions", "rewards", "dones", "timeouts"):
         assert torch.equal(full[k], torch.cat([h1[k], h2[k]], dim=0)), k
-    assert torch.equal(a.state, b.state) and torch.equal(a.state, c.state)
+    assert _same_state(a.state, b.state) and _same_state(a.state, c.state)
     assert torch.allclose(full["stats"], h1["stats"] + h2["stats"], rtol=1e-9)
     _, seed_action = RO.rollout_seeds(21)
     lo, hi = (float(a.action_space.low[0]), float(a.action_space.high[0])) if cont else (0, 1)
@@ -813,3 +857,57 @@ def test_rollout_ip_reset_samples_and_wrap():
             ref = RO.reset_sample_gaussian(idx[:16], ep_idx[idx[:16]], seed_reset, np.zeros(4), sp)
             assert np.allclose(obs[t + 1][idx[:16]], ref, rtol=0, atol=1e-9)
     assert dones.any()
+
+
+@pytest.mark.parametrize("env_id,cont", (("ChargedBallCentering-v0", False), ("ContinuousChargedBallCentering-v0", True)))
+def test_rollout_charged_ball_equals_step_kernel(env_id, cont):
+    """A charged-ball rollout = T calls of the (oracle-pinned) step kernel, bit for bit, plus the TimeLimit
+    bookkeeping of zoo/util.py:58-73 and in-kernel resets equal to charged_ball.py:84-94 on the Philox mirror."""
+    # long enough for take-offs and landings (both branches + free_to_circle); weaker continuous fields need longer
+    n, fr = 1024, 2
+    T, max_steps = (180, 100) if cont else (70, 30)
+    env = E.make(env_id, num_envs=n, dtype=torch.float32, freq_rate=fr)
+    ref = E.make(env_id, num_envs=n, dtype=torch.float32, freq_rate=fr)
+    env.reset(seed=5)
+    ref.state = {k: v.clone() for k, v in env.state.items()}
+    rng = np.random.default_rng(2)
+    if cont:  # strong fields, else the ball never leaves the ring within an episode
+        acts = (rng.choice([-1.0, 1.0], size=(T, n)) * rng.uniform(0.7, 1.0, size=(T, n))).astype(np.float32)
+    else:
+        acts = rng.integers(0, 2, size=(T, n)).astype(np.uint8)
+    out = env.rollout(T, actions=acts, record=True, max_episode_steps=max_steps)
+    obs, nxt, rew = (out[k].cpu().numpy() for k in ("observations", "next_observations", "rewards"))
+    dones, tmo = out["dones"].cpu().numpy(), out["timeouts"].cpu().numpy()
+    assert np.array_equal(out["actions"].cpu().numpy(), acts) and np.array_equal(dones, tmo)
+    seed_reset, _ = RO.rollout_seeds(5)
+    ep_step, ep_idx = np.zeros(n, np.int64), np.zeros(n, np.int64)
+    saw_free = False
+    for t in range(T):
+        assert np.array_equal(obs[t], ref.state["free_state"].cpu().numpy())
+        o2, r2, d2, _, _ = ref.step(acts[t])
+        assert np.array_equal(o2.cpu().numpy(), nxt[t]) and np.array_equal(r2.cpu().numpy()[:, 0], rew[t])
+        assert not d2.any()
+        saw_free |= bool((ref.state["on_circle"] == 0).any())
+        ep_step += 1
+        trunc = ep_step >= max_steps
+        assert np.array_equal(tmo[t], trunc)
+        idx = np.nonzero(trunc)[0]
+        if idx.size:
+            ep_idx[idx] += 1
+            on, circle, free = RO.reset_sample_charged_ball(idx, ep_idx[idx], seed_reset)
+            got_free = (obs[t + 1] if t + 1 < T else env.state["free_state"].cpu().numpy())[idx]
+            assert np.allclose(got_free, free, rtol=0, atol=3e-7)
+            st = {k: v.clone() for k, v in ref.state.items()}
+            j = torch.as_tensor(idx, device=st["circle_state"].device)
+            st["on_circle"][j] = 1
+            st["circle_state"][j] = torch.as_tensor(circle, device=j.device)
+            st["free_state"][j] = torch.as_tensor(got_free, device=j.device)
+            ref.state = st
+            ep_step[idx] = 0
+    assert saw_free and tmo.any()
+    assert _same_state(env.state, ref.state)
+    info = env.rollout_info(out["stats"])
+    assert info["truncated"] == int(tmo.sum()) == info["total_episode_num"] and info["terminated"] == 0
+    assert abs(info["avg_length"] - max_steps) < 1e-9
+    assert abs(info["reward_sum"] - float(rew.astype(np.float64).sum())) < 1e-3 * max(1.0, abs(float(rew.sum())))
+    assert np.array_equal(env._engine.ep_step.cpu().numpy(), ep_step) and np.array_equal(env._engine.ep_index.cpu().numpy(), ep_idx)
