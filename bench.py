@@ -210,7 +210,7 @@ class CartPoleStep(Workload):
     env_id, n_envs, freq_rate, ring = "ContinuousCartPoleSwingUp-v0", 1 << 20, 4, 8
     alg_bytes = 41  # state 16 + action 4 + next 16 + reward 4 + done 1
     cpu_kind = "c2"
-    inst_per_unit = 250.0  # warp-level SASS instructions per env-step, from ncu smsp__inst_executed (profiles/)
+    inst_per_unit = 209.0  # warp-level SASS instructions per env-step (packed f32x2: one FFMA2 serves two envs), ncu smsp__inst_executed (profiles/)
 
     def synth(self, seed):
         return synth_cartpole(self.n_envs, seed)

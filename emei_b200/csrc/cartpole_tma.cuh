@@ -1,0 +1,345 @@
+// float32 cart-pole / analytic inverted-pendulum step, TMA-staged: the shape used for every batch that is
+// 16-byte aligned (the per-thread cp.async kernel of cartpole_f32.cuh remains for misaligned action arrays).
+//
+// At BASELINE configs[1] (2^20 envs, 41 B/env-step) one SM's share of a step is 7 085 envs = 142 KB of inputs:
+// it FITS in the SM's 227 KB of shared memory.  So the kernel is one persistent CTA per SM whose producer warp
+// issues, at t = 0, one 1-D bulk copy (cp.async.bulk, the TMA engine) per 512-env chunk for as many chunks as the
+// ring holds -- every input byte of the step is in flight within the first microsecond, HBM streams at full
+// rate from the start, and no thread spends instructions or LDGSTS slots on address generation -- while three
+// consumer groups of 256 threads each take chunks as their mbarriers complete, advance TWO envs per thread
+// with the packed f32x2 arithmetic of f32math.cuh and store the results.  Larger batches recycle the ring
+// (empty mbarriers).  For a step kernel this short (~9 us) the ramp matters as much as the steady state:
+// per-thread prefetch rings issue a slot's refill only after that slot's math, which left HBM idle during
+// the compute of the first chunks (ncu: dram 18 %, issue 55 %, profiles/r01_ncu_kb_packed.txt).
+//
+// Chunk c = envs [512 c, 512 c + 512): thread t of a group owns envs 512 c + t and 512 c + 256 + t.
+#pragma once
+#include "cartpole_f32.cuh"
+
+namespace emei {
+
+constexpr int kTmaGroups = 4;                                 // consumer groups per CTA
+constexpr int kTmaConsumers = kTmaGroups * kBlock;            // 1024 threads: 8 warps per scheduler at <= 64 registers
+constexpr int kTmaThreads = kTmaConsumers;                    // thread 0 doubles as the TMA producer
+constexpr uint32_t kChunk = 2 * kBlock;                       // envs per chunk
+constexpr int kTmaSmemBudget = 208 * 1024;                    // ring bytes (of 227 KB per SM)
+constexpr int kTmaMaxSlots = 24;
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+// 1-D bulk copy global -> shared (TMA engine); completes `bytes` on the mbarrier.  16-byte aligned, size % 16 == 0.
+__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+template <bool IP, int AK, int FR, bool HAS_OBS>
+__global__ void __launch_bounds__(kTmaThreads, 1)
+    cartpole_step_f32_tma_kernel(const float4* state_in, float4* state_out, float4* obs_out,
+                                 const void* __restrict__ action, float* __restrict__ reward, uint8_t* __restrict__ done,
+                                 double* stats, uint32_t n, int n_slots, int action_via_tma, const CartPoleF32Consts k) {
+  using f32::f2;
+  using ActT = typename ActionStorage<AK>::type;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  // layout: [n_slots] state chunks (8 KB each) | [n_slots] action chunks | full[n_slots] | empty[n_slots] | reduction scratch
+  float4* s_state = reinterpret_cast<float4*>(smem_raw);
+  ActT* s_act = reinterpret_cast<ActT*>(smem_raw + static_cast<size_t>(n_slots) * kChunk * sizeof(float4));
+  uint64_t* full = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(s_act) + static_cast<size_t>(n_slots) * kChunk * sizeof(ActT));
+  uint64_t* empty = full + n_slots;
+  const uint32_t tid = threadIdx.x;
+  const uint32_t n_chunks = (n + kChunk - 1) / kChunk;
+  // this CTA's chunks: blockIdx.x, blockIdx.x + gridDim.x, ...   (local index j)
+  const uint32_t my_chunks = blockIdx.x < n_chunks ? (n_chunks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const ActT* act = static_cast<const ActT*>(action);
+
+  if (tid == 0) {
+    for (int s = 0; s < n_slots; ++s) {
+      mbar_init(&full[s], 1);                    // one arrive.expect_tx by the producer; the bytes complete it
+      mbar_init(&empty[s], kBlock / 32);         // one arrive per consumer warp of the group that drained the slot
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  pdl_trigger();  // let the next step kernel of the rollout be staged behind this one
+  __syncthreads();
+  pdl_wait();     // the previous kernel in the stream (the step that wrote state_in) has completed
+
+  float r_acc = 0.0f;
+  unsigned d_cnt = 0;
+  // ---- producer state (thread 0 only): chunks [0, issued) of this CTA have had their bulk copies issued
+  uint32_t issued = 0, p_phase = 0;  // p_phase: parity of the producer slot's CURRENT use
+  int p_slot = 0;
+  auto issue_until = [&](uint32_t upto) {
+    for (; issued < upto; ++issued) {
+      const uint32_t c = blockIdx.x + issued * gridDim.x;
+      const uint32_t base = c * kChunk;
+      const uint32_t cnt = n - base < kChunk ? n - base : kChunk;
+      if (issued >= static_cast<uint32_t>(n_slots)) mbar_wait(&empty[p_slot], p_phase ^ 1u);  // previous use drained
+      const bool act_tma = action_via_tma && cnt == kChunk;  // partial tail: consumers read their actions directly
+      const uint32_t sbytes = cnt * static_cast<uint32_t>(sizeof(float4));
+      const uint32_t abytes = act_tma ? kChunk * static_cast<uint32_t>(sizeof(ActT)) : 0u;
+      mbar_expect_tx(&full[p_slot], sbytes + abytes);
+      tma_load_1d(s_state + static_cast<size_t>(p_slot) * kChunk, state_in + base, sbytes, &full[p_slot]);
+      if (act_tma) tma_load_1d(s_act + static_cast<size_t>(p_slot) * kChunk, act + base, abytes, &full[p_slot]);
+      if (++p_slot == n_slots) {
+        p_slot = 0;
+        p_phase ^= 1u;
+      }
+    }
+  };
+  if (tid == 0) issue_until(my_chunks < static_cast<uint32_t>(n_slots) ? my_chunks : static_cast<uint32_t>(n_slots));
+  {
+    // ------------------------------------------------------------------ consumers: group g takes local chunks g, g+4, ...
+    const uint32_t g = tid / kBlock, t = tid % kBlock;
+    const uint32_t flip = ip_flip(IP, k.variant);
+    int slot = static_cast<int>(g) % n_slots;
+    uint32_t phase = (g / static_cast<uint32_t>(n_slots)) & 1u;
+    for (uint32_t j = g; j < my_chunks; j += kTmaGroups) {
+      const uint32_t c = blockIdx.x + j * gridDim.x;
+      const uint32_t i = c * kChunk + t;  // env A; env B = i + kBlock
+      const bool live_a = i < n, live_b = i + kBlock < n;
+      const bool act_tma = action_via_tma && (n - c * kChunk >= kChunk);
+      if (tid == 0) {  // recycle drained slots: everything up to n_slots chunks ahead of the one consumed now
+        const uint32_t ahead = j + static_cast<uint32_t>(n_slots);
+        issue_until(my_chunks < ahead ? my_chunks : ahead);
+      }
+      mbar_wait(&full[slot], phase);
+      const float4* sl = s_state + static_cast<size_t>(slot) * kChunk;
+      float4 ya = live_a ? sl[t] : make_float4(0.f, 0.f, 0.f, 0.f);
+      float4 yb = live_b ? sl[t + kBlock] : make_float4(0.f, 0.f, 0.f, 0.f);
+      float aa = 0.f, ab = 0.f;
+      if (act_tma) {
+        const ActT* sa = s_act + static_cast<size_t>(slot) * kChunk;
+        aa = static_cast<float>(sa[t]);
+        ab = static_cast<float>(sa[t + kBlock]);
+      } else {
+        if (live_a) aa = static_cast<float>(__ldg(act + i));
+        if (live_b) ab = static_cast<float>(__ldg(act + i + kBlock));
+      }
+      __syncwarp();
+      if ((t & 31u) == 0) mbar_arrive(&empty[slot]);  // this warp's reads of the slot are done
+      slot += kTmaGroups;
+      while (slot >= n_slots) {
+        slot -= n_slots;
+        phase ^= 1u;
+      }
+
+      const float fa = action_to_f_mt<IP, AK>(aa, k), fb = action_to_f_mt<IP, AK>(ab, k);
+      // ---- packed integration: [x, x_dot, theta, theta_dot] (cart-pole) / [x, theta, v, omega] (IP)
+      f2 X = f32::f2_pack(ya.x, yb.x), V, TH, W = f32::f2_pack(ya.w, yb.w);
+      if constexpr (!IP) {
+        V = f32::f2_pack(ya.y, yb.y);
+        TH = f32::f2_pack(ya.z, yb.z);
+      } else {
+        TH = f32::f2_pack(ya.y, yb.y);
+        V = f32::f2_pack(ya.z, yb.z);
+      }
+      const f2 nf = f32::f2_pack(-fa, -fb);
+      float tma = fabsf(IP ? ya.y : ya.z), tmb = fabsf(IP ? yb.y : yb.z);
+      const int fr = FR > 0 ? FR : k.freq_rate;
+#pragma unroll
+      for (int sub = 0; sub < fr; ++sub) {
+        f32::cartpole_substep2(X, V, TH, W, nf, flip, k.k);
+        float ta, tb;
+        f32::f2_unpack(TH, ta, tb);
+        tma = fmaxf(tma, fabsf(ta));
+        tmb = fmaxf(tmb, fabsf(tb));
+      }
+      float4 na, nb;
+      {
+        float t0, t1;
+        f32::f2_unpack(X, na.x, nb.x);
+        f32::f2_unpack(W, na.w, nb.w);
+        f32::f2_unpack(V, t0, t1);
+        if constexpr (!IP) { na.y = t0; nb.y = t1; } else { na.z = t0; nb.z = t1; }
+        f32::f2_unpack(TH, t0, t1);
+        if constexpr (!IP) { na.z = t0; nb.z = t1; } else { na.y = t0; nb.y = t1; }
+      }
+      // the unguarded sincos is valid while |theta| stays below kSinCosSaneMax; otherwise (or NaN) redo that
+      // env from its stored state with the libm path.  Cold: float32 theta is meaningless there.
+      const bool sane_a = tma <= f32::kSinCosSaneMax, sane_b = tmb <= f32::kSinCosSaneMax;
+      bool have_cos = true;
+      if (!(sane_a && sane_b)) {
+        have_cos = false;
+        if (!sane_a && live_a) {
+          na = state_in[i];
+          integrate<IP, FR, true>(na, fa, flip, k);
+        }
+        if (!sane_b && live_b) {
+          nb = state_in[i + kBlock];
+          integrate<IP, FR, true>(nb, fb, flip, k);
+        }
+      }
+      // ---- reward angle cosine, packed (cart-pole swing-up: cos(theta); IP: cos(wrapped theta))
+      float ca = 0.f, cb = 0.f;
+      if (have_cos) {
+        if constexpr (!IP) {
+          if (k.variant == EMEI_CARTPOLE_SWINGUP) f32::f2_unpack(f32::cos_core(f32::f2_pack(na.z, nb.z)), ca, cb);
+        } else {
+          f32::f2_unpack(f32::cos_core(f32::f2_pack(wrap_pi_f32(na.y), wrap_pi_f32(nb.y))), ca, cb);
+        }
+      }
+      float rew_a, rew_b;
+      bool nd_a, nd_b;
+      float4 oa, ob;
+      cartpole_outcome<IP>(na, sane_a, have_cos, ca, k, rew_a, nd_a, oa);
+      cartpole_outcome<IP>(nb, sane_b, have_cos, cb, k, rew_b, nd_b, ob);
+      if (live_a) {
+        state_out[i] = na;
+        if constexpr (HAS_OBS) obs_out[i] = oa;
+        reward[i] = rew_a;
+        done[i] = nd_a ? 0 : 1;
+        r_acc += rew_a;
+        d_cnt += nd_a ? 0u : 1u;
+      }
+      if (live_b) {
+        state_out[i + kBlock] = nb;
+        if constexpr (HAS_OBS) obs_out[i + kBlock] = ob;
+        reward[i + kBlock] = rew_b;
+        done[i + kBlock] = nd_b ? 0 : 1;
+        r_acc += rew_b;
+        d_cnt += nd_b ? 0u : 1u;
+      }
+    }
+  }
+  // ---- statistics: warp shuffles -> shared -> one atomic pair per CTA
+  if (stats != nullptr) {  // uniform across the grid
+    double* s_r = reinterpret_cast<double*>(empty + n_slots);
+    unsigned* s_d = reinterpret_cast<unsigned*>(s_r + kTmaThreads / 32);
+    const int lane = tid & 31, warp = tid >> 5;
+    const double r = warp_sum(static_cast<double>(r_acc));
+    const unsigned d = __reduce_add_sync(0xffffffffu, d_cnt);
+    if (lane == 0) {
+      s_r[warp] = r;
+      s_d[warp] = d;
+    }
+    __syncthreads();
+    if (warp == 0) {
+      double rr = lane < kTmaThreads / 32 ? s_r[lane] : 0.0;
+      unsigned dd = lane < kTmaThreads / 32 ? s_d[lane] : 0u;
+      rr = warp_sum(rr);
+      dd = __reduce_add_sync(0xffffffffu, dd);
+      if (lane == 0) {
+        atomicAdd(&stats[0], rr);
+        atomicAdd(&stats[1], static_cast<double>(dd));  // exact: counts << 2^53
+      }
+    }
+  }
+}
+
+// slots, dynamic shared memory bytes for an action element size
+inline void tma_ring_shape(int action_bytes, int64_t chunks_per_cta, int* n_slots, size_t* smem_bytes) {
+  const int slot_bytes = static_cast<int>(kChunk) * (16 + action_bytes);
+  int s = kTmaSmemBudget / slot_bytes;
+  if (s > kTmaMaxSlots) s = kTmaMaxSlots;
+  if (s > chunks_per_cta) s = static_cast<int>(chunks_per_cta);
+  if (s < kTmaGroups) s = kTmaGroups;
+  *n_slots = s;
+  *smem_bytes = static_cast<size_t>(s) * slot_bytes + 2 * s * sizeof(uint64_t) + (kTmaThreads / 32) * (sizeof(double) + sizeof(unsigned)) + 16;
+}
+
+template <auto Kernel>
+inline void tma_allow_smem() {  // opt in to > 48 KB of dynamic shared memory, once per kernel instantiation
+  static const bool once = []() {
+    cudaFuncSetAttribute(Kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    return true;
+  }();
+  (void)once;
+}
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl_smem(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t stream, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(static_cast<unsigned>(grid), 1, 1);
+  cfg.blockDim = dim3(static_cast<unsigned>(block), 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+template <bool IP, int FR>
+inline void launch_cartpole_f32_tma(int ak, cudaStream_t s, const float* state_in, float* state_out, float* obs_out,
+                                    const void* action, int action_bytes, float* reward, uint8_t* done, double* stats,
+                                    int64_t n, const CartPoleF32Consts& k) {
+  for (int64_t off = 0; off < n; off += kCartPoleMaxLaunch) {
+    const int64_t m = n - off < kCartPoleMaxLaunch ? n - off : kCartPoleMaxLaunch;
+    const int64_t chunks = (m + kChunk - 1) / kChunk;
+    const int grid = static_cast<int>(chunks < kNumSMs ? chunks : kNumSMs);
+    int n_slots;
+    size_t smem;
+    tma_ring_shape(action_bytes, (chunks + grid - 1) / grid, &n_slots, &smem);
+    const float4* in4 = reinterpret_cast<const float4*>(state_in) + off;
+    float4* out4 = reinterpret_cast<float4*>(state_out) + off;
+    float4* obs4 = obs_out ? reinterpret_cast<float4*>(obs_out) + off : nullptr;
+    const void* act = static_cast<const char*>(action) + off * action_bytes;
+    const int act_tma = (reinterpret_cast<uintptr_t>(act) & 15u) == 0 ? 1 : 0;
+    switch (ak) {
+#define EMEI_AK(A)                                                                                                       \
+  case A:                                                                                                                \
+    if (obs4 != nullptr) {                                                                                               \
+      tma_allow_smem<cartpole_step_f32_tma_kernel<IP, A, FR, true>>();                                                     \
+      launch_pdl_smem(cartpole_step_f32_tma_kernel<IP, A, FR, true>, grid, kTmaThreads, smem, s, in4, out4, obs4, act,   \
+                      reward + off, done + off, stats, static_cast<uint32_t>(m), n_slots, act_tma, k);                   \
+    } else {                                                                                                             \
+      tma_allow_smem<cartpole_step_f32_tma_kernel<IP, A, FR, false>>();                                                    \
+      launch_pdl_smem(cartpole_step_f32_tma_kernel<IP, A, FR, false>, grid, kTmaThreads, smem, s, in4, out4, obs4, act,  \
+                      reward + off, done + off, stats, static_cast<uint32_t>(m), n_slots, act_tma, k);                   \
+    }                                                                                                                    \
+    break;
+      EMEI_AK(EMEI_ACTION_DISCRETE_U8)
+      EMEI_AK(EMEI_ACTION_DISCRETE_I32)
+      EMEI_AK(EMEI_ACTION_DISCRETE_I64)
+      EMEI_AK(EMEI_ACTION_CONTINUOUS_F32)
+      EMEI_AK(EMEI_ACTION_CONTINUOUS_F64)
+#undef EMEI_AK
+    }
+  }
+}
+
+inline void cartpole_step_f32_tma_dispatch(const float* state_in, float* state_out, float* obs_out, const void* action,
+                                           float* reward, uint8_t* done, double* stats, int64_t n,
+                                           const emei_cartpole_params& p, cudaStream_t s) {
+  const CartPoleF32Consts k = make_cartpole_f32_consts(p);
+  const bool ip = p.variant > EMEI_CARTPOLE_SWINGUP;
+  const int ab = action_kind_bytes(p.action_kind);
+#define EMEI_GO(IPV, FRV) \
+  launch_cartpole_f32_tma<IPV, FRV>(p.action_kind, s, state_in, state_out, obs_out, action, ab, reward, done, stats, n, k)
+  if (!ip) {
+    if (p.freq_rate == 1) EMEI_GO(false, 1);
+    else if (p.freq_rate == 4) EMEI_GO(false, 4);
+    else EMEI_GO(false, 0);
+  } else {
+    if (p.freq_rate == 1) EMEI_GO(true, 1);
+    else if (p.freq_rate == 4) EMEI_GO(true, 4);
+    else EMEI_GO(true, 0);
+  }
+#undef EMEI_GO
+}
+
+}  // namespace emei

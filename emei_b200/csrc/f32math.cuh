@@ -77,55 +77,157 @@ constexpr float kSinCosSaneMax = 4.0e6f;  // |x * 2/pi| < 2^22: the magic-number
 constexpr float kS0 = -1.6666654611e-1f, kS1 = 8.3321608736e-3f, kS2 = -1.9515295891e-4f;
 constexpr float kC0 = 4.166664568298827e-2f, kC1 = -1.388731625493765e-3f, kC2 = 2.443315711809948e-5f;
 
-struct Reduced {
-  float r;     // x - j*pi/2, |r| <= pi/4 (+ rounding)
-  uint32_t q;  // j mod 4 (two's complement low bits)
+// ---------------------------------------------------------------------------------------------
+// One source for two instruction widths.  The arithmetic below is written over a value type V:
+//   V = float : scalar FFMA / FMUL / FADD (host and device; rollout kernels, charged ball, the host study)
+//   V = f2    : two envs per thread in one 64-bit register pair, Blackwell's packed fma/mul/add.rn.f32x2
+//               (SASS FFMA2 / FMUL2 / FADD2): one issue slot does the FP work of two envs.  The step kernel
+//               is bound by warp-instruction issue (ncu: issue 75 %, fma pipe 43 %, alu pipe 36 %), and
+//               FFMA2 occupies the fma pipe for two cycles but the scheduler for one, so packing moves the
+//               bound from "issue slots" (~250 / env-step) to "fma-pipe cycles" (~135 / env-step).
+// Every f32x2 lane is an IEEE fma.rn / mul.rn / add.rn, so V = f2 produces exactly the bits of V = float:
+// expressions are arranged so that no negation of a packed value is needed (negated constants / negated
+// intermediates commute with round-to-nearest).
+// ---------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ float vfma(float a, float b, float c) { return fmaf(a, b, c); }
+#if EMEI_F32_DEVICE
+__host__ __device__ __forceinline__ float vmul(float a, float b) { return __fmul_rn(a, b); }
+__host__ __device__ __forceinline__ float vadd(float a, float b) { return __fadd_rn(a, b); }
+#else
+__host__ __device__ __forceinline__ float vmul(float a, float b) { return a * b; }
+__host__ __device__ __forceinline__ float vadd(float a, float b) { return a + b; }
+#endif
+template <class V>
+struct Splat;
+template <>
+struct Splat<float> {
+  __host__ __device__ __forceinline__ static float of(float a) { return a; }
 };
-
-__host__ __device__ __forceinline__ Reduced reduce_pio2(float x) {
-  const float t = fmaf(x, kTwoOverPi, kRoundMagic);
-  const float j = t - kRoundMagic;
-  float r = fmaf(-j, kPio2Hi, x);
-  r = fmaf(-j, kPio2Mid, r);
-  r = fmaf(-j, kPio2Lo, r);
-  return {r, f2u(t)};
+#pragma nv_exec_check_disable
+template <class V>
+__host__ __device__ __forceinline__ V vsplat(float a) {
+  return Splat<V>::of(a);
 }
 
-__host__ __device__ __forceinline__ float sin_poly(float r, float r2) {
-  float p = fmaf(kS2, r2, kS1);
-  p = fmaf(p, r2, kS0);
-  return fmaf(r * r2, p, r);
+#ifdef __CUDACC__
+struct f2 {
+  unsigned long long v;  // {lo = env A, hi = env B}
+};
+__device__ __forceinline__ f2 f2_pack(float lo, float hi) {
+  f2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(lo), "f"(hi));
+  return r;
 }
-__host__ __device__ __forceinline__ float cos_poly(float r2) {
-  float p = fmaf(kC2, r2, kC1);
-  p = fmaf(p, r2, kC0);
-  p = fmaf(p, r2, -0.5f);
-  return fmaf(p, r2, 1.0f);
+__device__ __forceinline__ void f2_unpack(f2 a, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a.v)); }
+__device__ __forceinline__ f2 vfma(f2 a, f2 b, f2 c) {
+  f2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d.v) : "l"(a.v), "l"(b.v), "l"(c.v));
+  return d;
+}
+__device__ __forceinline__ f2 vmul(f2 a, f2 b) {
+  f2 d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d.v) : "l"(a.v), "l"(b.v));
+  return d;
+}
+__device__ __forceinline__ f2 vadd(f2 a, f2 b) {
+  f2 d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d.v) : "l"(a.v), "l"(b.v));
+  return d;
+}
+template <>
+struct Splat<f2> {
+  __device__ __forceinline__ static f2 of(float a) { return f2_pack(a, a); }
+};
+#endif
+
+// quadrant fix-up of one lane: (ps, pc) = (sin r, cos r) on the reduced argument, tbits = the bits of the
+// magic-number sum (low bits = j mod 4); flip = 0 or 0x80000000 negates both results (the analytic inverted
+// pendulum's swing-up models hang the pole down: theta_cartpole = theta + pi).
+__host__ __device__ __forceinline__ void quadrant_fix(float ps, float pc, uint32_t tbits, uint32_t flip, float* s, float* c) {
+  const bool swap = (tbits & 1u) != 0;
+  const float sv = swap ? pc : ps;
+  const float cv = swap ? ps : pc;
+  // quadrant signs: sin negative for q in {2,3}; cos negative for q in {1,2}
+  const uint32_t ssign = ((tbits & 2u) << 30) ^ flip;
+  const uint32_t csign = (((tbits + 1u) & 2u) << 30) ^ flip;
+  *s = u2f(f2u(sv) ^ ssign);
+  *c = u2f(f2u(cv) ^ csign);
+}
+
+// reduced argument r = x - j*pi/2 (|r| <= pi/4 + rounding) and t = x*2/pi + magic (its low bits hold j mod 4)
+#pragma nv_exec_check_disable
+template <class V>
+__host__ __device__ __forceinline__ void reduce_pio2(V x, V* r_out, V* t_out) {
+  const V t = vfma(x, vsplat<V>(kTwoOverPi), vsplat<V>(kRoundMagic));
+  const V j = vadd(t, vsplat<V>(-kRoundMagic));
+  V r = vfma(j, vsplat<V>(-kPio2Hi), x);
+  r = vfma(j, vsplat<V>(-kPio2Mid), r);
+  r = vfma(j, vsplat<V>(-kPio2Lo), r);
+  *r_out = r;
+  *t_out = t;
+}
+#pragma nv_exec_check_disable
+template <class V>
+__host__ __device__ __forceinline__ V sin_poly(V r, V r2) {
+  V p = vfma(vsplat<V>(kS2), r2, vsplat<V>(kS1));
+  p = vfma(p, r2, vsplat<V>(kS0));
+  return vfma(vmul(r, r2), p, r);
+}
+#pragma nv_exec_check_disable
+template <class V>
+__host__ __device__ __forceinline__ V cos_poly(V r2) {
+  V p = vfma(vsplat<V>(kC2), r2, vsplat<V>(kC1));
+  p = vfma(p, r2, vsplat<V>(kC0));
+  p = vfma(p, r2, vsplat<V>(-0.5f));
+  return vfma(p, r2, vsplat<V>(1.0f));
 }
 
 // sin and cos of x WITHOUT a range guard: valid (and ~1 ulp) for |x| <= 1e5, sane (quadrant-correct,
 // error growing to ~3e-6, far below the float32 spacing of x there) up to kSinCosSaneMax; NaN/Inf -> NaN.
 // Callers guard once per env step (see cartpole_f32.cuh), not once per evaluation.
-__host__ __device__ __forceinline__ void sincos_core(float x, float* s, float* c) {
-  const Reduced m = reduce_pio2(x);
-  const float r2 = m.r * m.r;
-  const float ps = sin_poly(m.r, r2);
-  const float pc = cos_poly(r2);
-  const bool swap = (m.q & 1u) != 0;
-  const float sv = swap ? pc : ps;
-  const float cv = swap ? ps : pc;
-  // quadrant signs: sin negative for q in {2,3}; cos negative for q in {1,2}
-  const uint32_t ssign = (m.q & 2u) << 30;
-  const uint32_t csign = ((m.q + 1u) & 2u) << 30;
-  *s = u2f(f2u(sv) ^ ssign);
-  *c = u2f(f2u(cv) ^ csign);
+__host__ __device__ __forceinline__ void sincos_core(float x, float* s, float* c, uint32_t flip = 0u) {
+  float r, t;
+  reduce_pio2<float>(x, &r, &t);
+  const float r2 = vmul(r, r);
+  quadrant_fix(sin_poly<float>(r, r2), cos_poly<float>(r2), f2u(t), flip, s, c);
 }
 __host__ __device__ __forceinline__ float cos_core(float x) {
-  const Reduced m = reduce_pio2(x);
-  const float r2 = m.r * m.r;
-  const float v = (m.q & 1u) ? sin_poly(m.r, r2) : cos_poly(r2);
-  return u2f(f2u(v) ^ (((m.q + 1u) & 2u) << 30));
+  float r, t;
+  reduce_pio2<float>(x, &r, &t);
+  const float r2 = vmul(r, r);
+  const uint32_t q = f2u(t);
+  const float v = (q & 1u) ? sin_poly<float>(r, r2) : cos_poly<float>(r2);
+  return u2f(f2u(v) ^ (((q + 1u) & 2u) << 30));
 }
+#ifdef __CUDACC__
+__device__ __forceinline__ void sincos_core(f2 x, f2* s, f2* c, uint32_t flip = 0u) {
+  f2 r, t;
+  reduce_pio2<f2>(x, &r, &t);
+  const f2 r2 = vmul(r, r);
+  const f2 ps = sin_poly<f2>(r, r2), pc = cos_poly<f2>(r2);
+  float psa, psb, pca, pcb, ta, tb, sa, sb, ca, cb;
+  f2_unpack(ps, psa, psb);
+  f2_unpack(pc, pca, pcb);
+  f2_unpack(t, ta, tb);
+  quadrant_fix(psa, pca, f2u(ta), flip, &sa, &ca);
+  quadrant_fix(psb, pcb, f2u(tb), flip, &sb, &cb);
+  *s = f2_pack(sa, sb);
+  *c = f2_pack(ca, cb);
+}
+__device__ __forceinline__ f2 cos_core(f2 x) {  // both lanes evaluate both polynomials (packed), then select
+  f2 r, t;
+  reduce_pio2<f2>(x, &r, &t);
+  const f2 r2 = vmul(r, r);
+  const f2 ps = sin_poly<f2>(r, r2), pc = cos_poly<f2>(r2);
+  float psa, psb, pca, pcb, ta, tb;
+  f2_unpack(ps, psa, psb);
+  f2_unpack(pc, pca, pcb);
+  f2_unpack(t, ta, tb);
+  const uint32_t qa = f2u(ta), qb = f2u(tb);
+  const float va = (qa & 1u) ? psa : pca, vb = (qb & 1u) ? psb : pcb;
+  return f2_pack(u2f(f2u(va) ^ (((qa + 1u) & 2u) << 30)), u2f(f2u(vb) ^ (((qb + 1u) & 2u) << 30)));
+}
+#endif
 
 __host__ __device__ __forceinline__ void sincos_libm(float x, float* s, float* c) {
 #if EMEI_F32_DEVICE
@@ -160,26 +262,55 @@ struct CartPoleK {
   float g, kpm /* pml/mt */, inv_mt, den0 /* l*4/3 */, den1 /* l*mp/mt */, dt;
 };
 
+__host__ __device__ __forceinline__ float vrcp(float x) { return rcp_fast(x); }
+#ifdef __CUDACC__
+__device__ __forceinline__ f2 vrcp(f2 x) {
+  float a, b;
+  f2_unpack(x, a, b);
+  return f2_pack(rcp_fast(a), rcp_fast(b));
+}
+#endif
+
+// One forward-Euler sub-step given (s, c) = (sin, cos) of the CART-POLE angle.  nf_mt = -(force / m_total).
+// Written with -temp and -x_acc so that the packed form needs no negation; bit for bit
+//   temp = fma(kpm*(w*w), s, f_mt); num = fma(g, s, -(c*temp)); den = fma(-den1, c*c, den0);
+//   th_acc = num * rcp(den); x_acc = fma(-kpm, th_acc*c, temp); x += xd*dt; xd += x_acc*dt; th += w*dt; w += th_acc*dt
+#pragma nv_exec_check_disable
+template <class V>
+__host__ __device__ __forceinline__ void cartpole_euler(V& x, V& xd, V& th, V& w, V s, V c, V nf_mt, const CartPoleK& k) {
+  const V ntemp = vfma(vmul(vsplat<V>(-k.kpm), vmul(w, w)), s, nf_mt);
+  const V num = vfma(vsplat<V>(k.g), s, vmul(c, ntemp));
+  const V den = vfma(vsplat<V>(-k.den1), vmul(c, c), vsplat<V>(k.den0));
+  const V th_acc = vmul(num, vrcp(den));
+  const V nx_acc = vfma(vsplat<V>(k.kpm), vmul(th_acc, c), ntemp);
+  const V dt = vsplat<V>(k.dt);
+  x = vfma(xd, dt, x);
+  xd = vfma(nx_acc, vsplat<V>(-k.dt), xd);
+  th = vfma(w, dt, th);
+  w = vfma(th_acc, dt, w);
+}
+
+// sub-step of the state (x, xd, th, w).  flip = 0x80000000 for the inverted pendulum's hanging models.
 template <bool LIBM>
 __host__ __device__ __forceinline__ void cartpole_substep(float& x, float& xd, float& th, float& w, float f_mt,
-                                                          float sgn, const CartPoleK& k) {
+                                                          uint32_t flip, const CartPoleK& k) {
   float s, c;
-  if (LIBM)
+  if (LIBM) {
     sincos_libm(th, &s, &c);
-  else
-    sincos_core(th, &s, &c);
-  s *= sgn;  // analytic inverted pendulum (swing-up models hang the pole down): theta_cartpole = theta + pi
-  c *= sgn;
-  const float temp = fmaf(k.kpm * (w * w), s, f_mt);
-  const float num = fmaf(k.g, s, -(c * temp));
-  const float den = fmaf(-k.den1, c * c, k.den0);
-  const float th_acc = num * rcp_fast(den);
-  const float x_acc = fmaf(-k.kpm, th_acc * c, temp);
-  x = fmaf(xd, k.dt, x);
-  xd = fmaf(x_acc, k.dt, xd);
-  th = fmaf(w, k.dt, th);
-  w = fmaf(th_acc, k.dt, w);
+    s = u2f(f2u(s) ^ flip);
+    c = u2f(f2u(c) ^ flip);
+  } else {
+    sincos_core(th, &s, &c, flip);
+  }
+  cartpole_euler<float>(x, xd, th, w, s, c, -f_mt, k);
 }
+#ifdef __CUDACC__
+__device__ __forceinline__ void cartpole_substep2(f2& x, f2& xd, f2& th, f2& w, f2 nf_mt, uint32_t flip, const CartPoleK& k) {
+  f2 s, c;
+  sincos_core(th, &s, &c, flip);
+  cartpole_euler<f2>(x, xd, th, w, s, c, nf_mt, k);
+}
+#endif
 
 }  // namespace f32
 }  // namespace emei

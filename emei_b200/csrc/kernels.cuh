@@ -174,8 +174,8 @@ int cartpole_step(const R* state_in, R* state_out, R* obs_out, const void* actio
   if (obs_out) EMEI_CHECK_ALIGN16(obs_out);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
 #ifdef EMEI_HAVE_CARTPOLE_F32
-  if constexpr (sizeof(R) == 4) {  // lean float32 kernel (cartpole_f32.cuh)
-    cartpole_step_f32_dispatch(state_in, state_out, obs_out, action, reward, done, stats, n, *p, s);
+  if constexpr (sizeof(R) == 4) {  // lean float32 kernel: TMA-staged, packed f32x2 (cartpole_tma.cuh)
+    cartpole_step_f32_tma_dispatch(state_in, state_out, obs_out, action, reward, done, stats, n, *p, s);
     return launch_status();
   }
 #endif

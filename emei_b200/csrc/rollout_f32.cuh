@@ -115,55 +115,20 @@ struct CartPoleDyn {
   __device__ __forceinline__ static float4 observation(const Regs& e) {
     return IP ? make_float4(e.y.x, wrap_pi_f32(e.y.y), e.y.z, e.y.w) : e.y;
   }
-  // identical to the body of cartpole_step_f32_kernel
+  // the scalar (one env per thread) form of the arithmetic of cartpole_step_f32_tma_kernel: same bits
   __device__ __forceinline__ static void step(Regs& e, float a, const Consts& k, float& rew, bool& terminated, float4& next_obs) {
-    const bool swingup_ip = IP && (k.variant == EMEI_IP_REBOUND_SWINGUP || k.variant == EMEI_IP_BOUNDARY_SWINGUP);
-    const float sgn = swingup_ip ? -1.0f : 1.0f;
-    float f_mt;
-    if constexpr (!IP) {
-      float force;
-      if constexpr (kDiscrete)
-        force = a == 1.0f ? k.force_mag : -k.force_mag;
-      else
-        force = k.force_mag * a;
-      f_mt = force * k.k.inv_mt;
-    } else {
-      float ctrl = a;
-      ctrl = ctrl < k.ctrl_low ? k.ctrl_low : (ctrl > k.ctrl_high ? k.ctrl_high : ctrl);
-      f_mt = (k.force_mag * ctrl) * k.k.inv_mt;
-    }
+    const uint32_t flip = ip_flip(IP, k.variant);
+    const float f_mt = action_to_f_mt<IP, AK>(a, k);
     float4 y = e.y;
     const float4 y0 = y;
-    const float th_max = integrate<IP, FR, false>(y, f_mt, sgn, k);
+    const float th_max = integrate<IP, FR, false>(y, f_mt, flip, k);
     const bool sane = th_max <= f32::kSinCosSaneMax;
     if (!sane) {
       y = y0;
-      integrate<IP, FR, true>(y, f_mt, sgn, k);
+      integrate<IP, FR, true>(y, f_mt, flip, k);
     }
     bool notdone;
-    next_obs = y;
-    if constexpr (!IP) {
-      if (k.variant == EMEI_CARTPOLE_SWINGUP) {
-        const float cth = sane ? f32::cos_core(y.z) : cosf(y.z);
-        rew = fmaf(cth, 0.5f, 0.5f);
-        notdone = fabsf(y.x) < k.x_thr;
-      } else {
-        rew = 1.0f;
-        notdone = (fabsf(y.z) < k.th_thr) && (fabsf(y.x) < k.x_thr);
-      }
-    } else {
-      const float th_obs = wrap_pi_f32(y.y);
-      next_obs.y = th_obs;
-      const bool finite = isfinite(y.x) && isfinite(th_obs) && isfinite(y.z) && isfinite(y.w);
-      const float cy = f32::cos_core(th_obs);
-      const bool in_rail = (k.x_left < y.x) && (y.x < k.x_right);
-      switch (k.variant) {
-        case EMEI_IP_REBOUND_BALANCING: rew = 1.0f; notdone = (cy >= 0.9f) && finite; break;
-        case EMEI_IP_BOUNDARY_BALANCING: rew = 1.0f; notdone = (cy >= 0.0f) && in_rail && finite; break;
-        case EMEI_IP_REBOUND_SWINGUP: rew = fmaf(cy, -0.5f, 0.5f); notdone = finite; break;
-        default: rew = fmaf(cy, -0.5f, 0.5f); notdone = in_rail && finite; break;
-      }
-    }
+    cartpole_outcome<IP>(y, sane, false, 0.f, k, rew, notdone, next_obs);
     e.y = y;
     terminated = !notdone;
   }

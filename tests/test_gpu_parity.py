@@ -911,3 +911,41 @@ def test_rollout_charged_ball_equals_step_kernel(env_id, cont):
     assert abs(info["avg_length"] - max_steps) < 1e-9
     assert abs(info["reward_sum"] - float(rew.astype(np.float64).sum())) < 1e-3 * max(1.0, abs(float(rew.sum())))
     assert np.array_equal(env._engine.ep_step.cpu().numpy(), ep_step) and np.array_equal(env._engine.ep_index.cpu().numpy(), ep_idx)
+
+
+@pytest.mark.parametrize("env_id,cont,n", (
+    ("ContinuousCartPoleSwingUp-v0", True, 148 * 24 * 512 + 1234),   # > 24 chunks per SM: the TMA ring recycles its slots
+    ("CartPoleSwingUp-v0", False, 148 * 26 * 512 * 2 + 77),          # uint8 actions, two laps of the ring, ragged tail
+    ("BoundaryInvertedPendulumSwingUp-v0", True, 1 << 21),
+    ("CartPoleBalancing-v0", False, 513),                             # one full chunk + one env
+))
+def test_step_kernel_large_batches_equal_scalar_rollout(env_id, cont, n):
+    """The step kernel (TMA ring, packed f32x2, two envs per thread) against the scalar one-env-per-thread
+    arithmetic of the rollout kernel on the same inputs: bit for bit, at sizes that wrap the shared-memory ring,
+    with ragged tails; statistics equal the sums of the outputs."""
+    fr = 4
+    a = E.make(env_id, num_envs=n, dtype=torch.float32, freq_rate=fr)
+    b = E.make(env_id, num_envs=n, dtype=torch.float32, freq_rate=fr)
+    a.reset(seed=11)
+    g = torch.Generator(device=a.device)
+    g.manual_seed(5)
+    st = a.state.clone()
+    st.mul_(1.0 + 40.0 * torch.rand(st.shape, device=st.device, generator=g))  # spread the states out
+    a.state = st
+    b.state = st
+    act = (torch.rand(n, device=a.device, generator=g) * 2 - 1) if cont else torch.randint(0, 2, (n,), device=a.device, generator=g, dtype=torch.uint8)
+    a.reset_stats()
+    obs, rew, done, _, _ = a.step(act)
+    out = b.rollout(1, actions=act.reshape(1, n), record=True, auto_reset=False, max_episode_steps=0)
+    assert torch.equal(obs, out["next_observations"][0])
+    assert torch.equal(rew[:, 0], out["rewards"][0])
+    assert torch.equal(done[:, 0], out["dones"][0])
+    rs, dc = a.read_stats()
+    assert dc == int(done.sum()) and abs(rs - float(rew.double().sum())) <= 1e-6 * max(1.0, abs(rs))
+    # misaligned action array (element offset 1): the kernel reads actions directly instead of through TMA
+    act2 = torch.empty(n + 1, dtype=act.dtype, device=act.device)[1:]
+    act2.copy_(act)
+    c = E.make(env_id, num_envs=n, dtype=torch.float32, freq_rate=fr)
+    c.state = st
+    obs2, rew2, done2, _, _ = c.step(act2)
+    assert torch.equal(obs2, obs) and torch.equal(rew2, rew) and torch.equal(done2, done)

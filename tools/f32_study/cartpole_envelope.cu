@@ -59,7 +59,7 @@ int main(int argc, char** argv) {
     ref_step(y, (double)force, fr, dt);
     float x = st[0], xd = st[1], th = st[2], w = st[3];
     const float f_mt = force * k.inv_mt;
-    for (int j = 0; j < fr; ++j) emei::f32::cartpole_substep<false>(x, xd, th, w, f_mt, 1.0f, k);
+    for (int j = 0; j < fr; ++j) emei::f32::cartpole_substep<false>(x, xd, th, w, f_mt, 0u, k);
     float o[4] = {x, xd, th, w};
     for (int j = 0; j < 4; ++j) {
       double e = fabs((double)o[j] - y[j]) / (1e-6 + 1e-5 * fabs(y[j]));

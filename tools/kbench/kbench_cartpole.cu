@@ -5,9 +5,13 @@
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
-#include "../../emei_b200/csrc/cartpole_f32.cuh"
+#include "../../emei_b200/csrc/cartpole_tma.cuh"
+#include "cartpole_cpasync_variant.cuh"
 
 using namespace emei;
+#include <cstring>
+static const char* g_filter = nullptr;  // argv[4]: run only the variants whose name contains it
+#define SKIP(name) if (g_filter && !strstr(name, g_filter)) return
 
 #define CK(x) do { cudaError_t err_ = (x); if (err_ != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(err_), __FILE__, __LINE__); exit(1);} } while (0)
 
@@ -37,9 +41,29 @@ compute_kernel(float* out, uint32_t n, const CartPoleF32Consts k) {
   for (uint32_t i = blockIdx.x * kBlock + threadIdx.x; i < n; i += stride) {
     float4 y = make_float4(1e-6f * i, 0.5f, 2e-6f * i, -1.0f);
     const float f_mt = 1e-7f * i;
-    const float th_max = integrate<false, FR, false>(y, f_mt, 1.0f, k);
+    const float th_max = integrate<false, FR, false>(y, f_mt, 0u, k);
     const float rew = fmaf(f32::cos_core(y.z), 0.5f, 0.5f);
     acc += rew + y.x + y.y + y.w + th_max;
+  }
+  if (acc == 12345.678f) out[0] = acc;
+}
+
+// compute only, packed f32x2: two envs per thread (the arithmetic of the shipped step kernel)
+template <int MINB, int FR>
+__global__ void __launch_bounds__(kBlock, MINB)
+compute2_kernel(float* out, uint32_t n, const CartPoleF32Consts k) {
+  using f32::f2;
+  const uint32_t stride = gridDim.x * kBlock * 2;
+  float acc = 0.f;
+  for (uint32_t i = blockIdx.x * kBlock * 2 + threadIdx.x; i < n; i += stride) {
+    f2 X = f32::f2_pack(1e-6f * i, 2e-6f * i), V = f32::f2_pack(0.5f, 0.25f), TH = f32::f2_pack(2e-6f * i, 1e-6f * i), W = f32::f2_pack(-1.f, 1.f);
+    const f2 nf = f32::f2_pack(1e-7f * i, -1e-7f * i);
+#pragma unroll
+    for (int sub = 0; sub < FR; ++sub) f32::cartpole_substep2(X, V, TH, W, nf, 0u, k.k);
+    float a, b, c, d;
+    f32::f2_unpack(f32::cos_core(TH), a, b);
+    f32::f2_unpack(vadd(vadd(X, V), W), c, d);
+    acc += a + b + c + d;
   }
   if (acc == 12345.678f) out[0] = acc;
 }
@@ -78,7 +102,7 @@ cartpole_ilp2_kernel(const float4* state_in, float4* state_out, const float* __r
     for (int sub = 0; sub < 4; ++sub) {
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
-        f32::cartpole_substep<false>(y[e].x, y[e].y, y[e].z, y[e].w, f_mt[e], 1.0f, k.k);
+        f32::cartpole_substep<false>(y[e].x, y[e].y, y[e].z, y[e].w, f_mt[e], 0u, k.k);
         th_max[e] = fmaxf(th_max[e], fabsf(y[e].z));
       }
     }
@@ -130,12 +154,13 @@ float time_graph(F launch, int K, cudaStream_t s, int reps = 5) {
 
 template <int MINB, int FR, bool PDL, int S = 4, int DBG = 0>
 void run_cartpole(const char* name, Ring& R, uint32_t n, int K, cudaStream_t s, int grid_override = 0) {
+  SKIP(name);
   emei_cartpole_params p = {};
   p.gravity = 9.8; p.mass_pole = 0.1; p.total_mass = 1.1; p.length = 0.5; p.pole_mass_length = 0.05; p.force_mag = 10.0;
   p.x_threshold = 5.0; p.theta_threshold = 0.2; p.dt = 0.02; p.freq_rate = 4; p.variant = EMEI_CARTPOLE_SWINGUP;
   p.action_kind = EMEI_ACTION_CONTINUOUS_F32;
   CartPoleF32Consts k = make_cartpole_f32_consts(p);
-  int grid = grid_override ? grid_override : persistent_grid(n, kBlock, MINB);
+  int grid = grid_override ? grid_override : persistent_grid(n, 2 * kBlock, MINB);
   double* stats; CK(cudaMalloc(&stats, 16)); CK(cudaMemset(stats, 0, 16));
   const int ring = (int)R.in.size();
   auto launch = [&](int i) {
@@ -150,8 +175,36 @@ void run_cartpole(const char* name, Ring& R, uint32_t n, int K, cudaStream_t s, 
   cudaFree(stats);
 }
 
+template <int FR>
+void run_tma(const char* name, Ring& R, uint32_t n, int K, cudaStream_t s, int slots_cap = 0) {
+  SKIP(name);
+  emei_cartpole_params p = {};
+  p.gravity = 9.8; p.mass_pole = 0.1; p.total_mass = 1.1; p.length = 0.5; p.pole_mass_length = 0.05; p.force_mag = 10.0;
+  p.x_threshold = 5.0; p.theta_threshold = 0.2; p.dt = 0.02; p.freq_rate = 4; p.variant = EMEI_CARTPOLE_SWINGUP;
+  p.action_kind = EMEI_ACTION_CONTINUOUS_F32;
+  CartPoleF32Consts k = make_cartpole_f32_consts(p);
+  const int64_t chunks = (n + kChunk - 1) / kChunk;
+  const int grid = (int)(chunks < kNumSMs ? chunks : kNumSMs);
+  int n_slots; size_t smem;
+  tma_ring_shape(4, (chunks + grid - 1) / grid, &n_slots, &smem);
+  if (slots_cap && n_slots > slots_cap) { n_slots = slots_cap; smem = (size_t)n_slots * kChunk * 20 + 2 * n_slots * 8 + (kTmaThreads / 32) * 12 + 16; }
+  double* stats; CK(cudaMalloc(&stats, 16)); CK(cudaMemset(stats, 0, 16));
+  const int ring = (int)R.in.size();
+  auto kern = cartpole_step_f32_tma_kernel<false, EMEI_ACTION_CONTINUOUS_F32, FR, false>;
+  CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  auto launch = [&](int i) {
+    int j = i % ring;
+    launch_pdl_smem(kern, grid, kTmaThreads, smem, s, (const float4*)R.in[j], (float4*)R.out[j], (float4*)nullptr, (const void*)R.act[j], R.rew[j], R.done[j], stats, n, n_slots, 1, k);
+  };
+  float us = time_graph(launch, K, s);
+  CK(cudaGetLastError());
+  printf("%-44s grid=%5d  %7.2f us/launch  %6.1f Genv-steps/s  %6.0f GB/s (41 B/env)  slots=%d smem=%zu\n", name, grid, us, n / us * 1e-3, 41.0 * n / us * 1e-3, n_slots, smem);
+  cudaFree(stats);
+}
+
 template <int MINB, int S>
 void run_ilp2(const char* name, Ring& R, uint32_t n, int K, cudaStream_t s) {
+  SKIP(name);
   emei_cartpole_params p = {};
   p.gravity = 9.8; p.mass_pole = 0.1; p.total_mass = 1.1; p.length = 0.5; p.pole_mass_length = 0.05; p.force_mag = 10.0;
   p.x_threshold = 5.0; p.theta_threshold = 0.2; p.dt = 0.02; p.freq_rate = 4; p.variant = EMEI_CARTPOLE_SWINGUP;
@@ -171,6 +224,7 @@ void run_ilp2(const char* name, Ring& R, uint32_t n, int K, cudaStream_t s) {
 
 template <int MINB, int FR>
 void run_compute(const char* name, Ring& R, uint32_t n, int K, cudaStream_t s) {
+  SKIP(name);
   emei_cartpole_params p = {};
   p.gravity = 9.8; p.mass_pole = 0.1; p.total_mass = 1.1; p.length = 0.5; p.pole_mass_length = 0.05; p.force_mag = 10.0;
   p.x_threshold = 5.0; p.theta_threshold = 0.2; p.dt = 0.02; p.freq_rate = 4; p.variant = EMEI_CARTPOLE_SWINGUP;
@@ -182,8 +236,23 @@ void run_compute(const char* name, Ring& R, uint32_t n, int K, cudaStream_t s) {
   printf("%-44s grid=%5d  %7.2f us/launch\n", name, grid, us);
 }
 
+template <int MINB, int FR>
+void run_compute2(const char* name, Ring& R, uint32_t n, int K, cudaStream_t s) {
+  SKIP(name);
+  emei_cartpole_params p = {};
+  p.gravity = 9.8; p.mass_pole = 0.1; p.total_mass = 1.1; p.length = 0.5; p.pole_mass_length = 0.05; p.force_mag = 10.0;
+  p.x_threshold = 5.0; p.theta_threshold = 0.2; p.dt = 0.02; p.freq_rate = 4; p.variant = EMEI_CARTPOLE_SWINGUP;
+  CartPoleF32Consts k = make_cartpole_f32_consts(p);
+  int grid = persistent_grid(n, 2 * kBlock, MINB);
+  auto launch = [&](int i) { compute2_kernel<MINB, FR><<<grid, kBlock, 0, s>>>(R.rew[0], n, k); };
+  float us = time_graph(launch, K, s);
+  CK(cudaGetLastError());
+  printf("%-44s grid=%5d  %7.2f us/launch\n", name, grid, us);
+}
+
 template <int MINB, bool PDL>
 void run_stream(const char* name, Ring& R, uint32_t n, int K, cudaStream_t s) {
+  SKIP(name);
   int grid = persistent_grid(n, kBlock, MINB);
   const int ring = (int)R.in.size();
   auto launch = [&](int i) {
@@ -200,6 +269,8 @@ int main(int argc, char** argv) {
   const uint32_t n = argc > 1 ? (uint32_t)atol(argv[1]) : (1u << 20);
   const int ring = argc > 2 ? atoi(argv[2]) : 8;
   const int K = argc > 3 ? atoi(argv[3]) : 400;
+  if (argc > 4) g_filter = argv[4];
+  setvbuf(stdout, NULL, _IONBF, 0);
   cudaStream_t s; CK(cudaStreamCreate(&s));
   Ring R;
   std::vector<float> h(4 * (size_t)n), ha(n);
@@ -214,26 +285,25 @@ int main(int argc, char** argv) {
     R.in.push_back(a); R.out.push_back(b); R.act.push_back(c); R.rew.push_back(d); R.done.push_back(e);
   }
   printf("n=%u ring=%d K=%d\n", n, ring, K);
-  run_stream<8, false>("stream minb8", R, n, K, s);
   run_stream<8, true>("stream minb8 pdl", R, n, K, s);
-  run_stream<6, true>("stream minb6 pdl", R, n, K, s);
-  run_compute<6, 4>("compute-only fr4 minb6", R, n, K, s);
-  run_compute<8, 4>("compute-only fr4 minb8", R, n, K, s);
-  run_compute<4, 4>("compute-only fr4 minb4", R, n, K, s);
-  run_compute<6, 0>("compute-only fr-runtime minb6", R, n, K, s);
-  run_cartpole<4, 0, true>("cartpole fr-runtime minb4 pdl", R, n, K, s);
-  run_cartpole<5, 0, true>("cartpole fr-runtime minb5 pdl", R, n, K, s);
-  run_cartpole<8, 0, true>("cartpole fr-runtime minb8 pdl", R, n, K, s);
-  run_ilp2<4, 2>("ILP2 minb4 S2", R, n, K, s);
-  run_ilp2<4, 3>("ILP2 minb4 S3", R, n, K, s);
-  run_ilp2<3, 2>("ILP2 minb3 S2", R, n, K, s);
-  run_ilp2<3, 3>("ILP2 minb3 S3", R, n, K, s);
-  run_ilp2<2, 3>("ILP2 minb2 S3", R, n, K, s);
-  run_ilp2<2, 4>("ILP2 minb2 S4", R, n, K, s);
-  run_cartpole<4, 4, true, 4>("cartpole fr4 minb4 S4", R, n, K, s);
-  run_cartpole<4, 4, true, 4, 1>("cartpole fr4 minb4 S4 NO-STORE", R, n, K, s);
-  run_cartpole<4, 4, true, 4, 2>("cartpole fr4 minb4 S4 NO-LOAD", R, n, K, s);
-  run_cartpole<6, 4, true, 4, 1>("cartpole fr4 minb6 S4 NO-STORE", R, n, K, s);
-  run_cartpole<6, 4, true, 4, 2>("cartpole fr4 minb6 S4 NO-LOAD", R, n, K, s);
+  run_compute<4, 4>("compute-only scalar fr4 minb4", R, n, K, s);
+  run_compute2<2, 4>("compute-only packed fr4 minb2", R, n, K, s);
+  run_compute2<3, 4>("compute-only packed fr4 minb3", R, n, K, s);
+  run_compute2<4, 4>("compute-only packed fr4 minb4", R, n, K, s);
+  run_tma<4>("TMA packed fr4", R, n, K, s);
+  run_tma<4>("TMA packed fr4 slots<=8", R, n, K, s, 8);
+  run_tma<4>("TMA packed fr4 slots<=4", R, n, K, s, 4);
+  run_tma<0>("TMA packed fr-runtime", R, n, K, s);
+  run_cartpole<2, 4, true, 4>("cartpole packed fr4 minb2 S4", R, n, K, s);
+  run_cartpole<2, 4, true, 2>("cartpole packed fr4 minb2 S2", R, n, K, s);
+  run_cartpole<3, 4, true, 4>("cartpole packed fr4 minb3 S4", R, n, K, s);
+  run_cartpole<3, 4, true, 3>("cartpole packed fr4 minb3 S3", R, n, K, s);
+  run_cartpole<3, 4, true, 2>("cartpole packed fr4 minb3 S2", R, n, K, s);
+  run_cartpole<4, 4, true, 2>("cartpole packed fr4 minb4 S2", R, n, K, s);
+  run_cartpole<4, 4, true, 3>("cartpole packed fr4 minb4 S3", R, n, K, s);
+  run_cartpole<3, 4, true, 3, 1>("cartpole packed fr4 minb3 S3 NO-STORE", R, n, K, s);
+  run_cartpole<3, 4, true, 3, 2>("cartpole packed fr4 minb3 S3 NO-LOAD", R, n, K, s);
+  run_cartpole<3, 0, true, 2>("cartpole packed fr-runtime minb3 S2", R, n, K, s);
+  run_cartpole<4, 0, true, 2>("cartpole packed fr-runtime minb4 S2", R, n, K, s);
   return 0;
 }
