@@ -126,6 +126,7 @@ _PLAIN = {
     "emei_cartpole_rollout_f32": (c_int, [_P] * 12 + [c_int64, POINTER(CartPoleParams), POINTER(RolloutParams), _P]),
     "emei_charged_ball_rollout_f32": (c_int, [_P] * 14 + [c_int64, POINTER(ChargedBallParams), POINTER(RolloutParams), _P]),
     "emei_snapshot_copy": (c_int, [_P, _P, c_int64, _P]),
+    "emei_records_transpose": (c_int, [_P, _P, c_int64, c_int64, c_int32, _P]),
     "emei_stats_reset": (c_int, [_P, _P]),
     "emei_version": (c_int, []),
     "emei_error_string": (c_char_p, [c_int]),

@@ -5,8 +5,9 @@ argument meaning and error behaviour, with arrays generalised to ``[num_envs, di
 numpy inputs are accepted everywhere (copied to the device; results come back as numpy), so code
 written against the reference's ``get_batch_*`` keeps working unchanged.
 
-Out of scope: the offline-dataset download/h5 loader of
-``OfflineEnv`` (core.py:40-128) -- ``dataset_names`` is empty and ``get_dataset`` raises.
+``OfflineEnv`` (core.py:40-128): datasets are read from the reference's local cache layout
+(``emei_b200.offline``); the download step (``urllib``, core.py:94-107) is out of scope -- there is no network --
+so ``dataset_names`` lists what is on disk and ``get_dataset`` raises for anything that is not.
 """
 from typing import Dict, Union
 
@@ -130,10 +131,22 @@ class EmeiEnv(Freezable):
     # ------------------------------------------------------------------ core.py contract
     @property
     def dataset_names(self) -> list:
-        return []
+        """core.py:52-54: the names known for this env / parameter set -- here, the files present in the
+        reference's cache directory (core.py:83-92)."""
+        from . import offline
+
+        d = offline.dataset_path(self, "")
+        return sorted(p.name for p in d.iterdir() if p.suffix in (".h5", ".hdf5", ".npz")) if d.is_dir() else []
 
     def get_dataset(self, dataset_name: str):
-        raise NotImplementedError("offline h5 datasets (core.py:40-128) are outside the emei_b200 hot path")
+        """core.py:109-128 without the download (no network): loads ``DATASET_PATH/<env_name>/<env_params_name>/
+        <dataset_name>`` (.h5 needs h5py; .npz always works) and runs the reference's key checks."""
+        from . import offline
+
+        path = offline.dataset_path(self, dataset_name)
+        if not path.exists():
+            raise FileNotFoundError(f"{path} does not exist and emei_b200 does not download datasets (core.py:94-107)")
+        return offline.load_dataset(path)
 
     @property
     def env_params_name(self):

@@ -31,6 +31,22 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive_u32(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ void mbar_wait_u32(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (ok == 0);
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -113,6 +129,8 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
     // ------------------------------------------------------------------ consumers: group g takes local chunks g, g+4, ...
     const uint32_t g = tid / kBlock, t = tid % kBlock;
     const uint32_t flip = ip_flip(IP, k.variant);
+    // 32-bit shared-window addresses, computed once (the generic-pointer forms re-derive the window base per chunk)
+    const uint32_t state_u32 = smem_u32(s_state) + t * 16u, full_u32 = smem_u32(full), empty_u32 = smem_u32(empty);
     int slot = static_cast<int>(g) % n_slots;
     uint32_t phase = (g / static_cast<uint32_t>(n_slots)) & 1u;
     for (uint32_t j = g; j < my_chunks; j += kTmaGroups) {
@@ -124,10 +142,10 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
         const uint32_t ahead = j + static_cast<uint32_t>(n_slots);
         issue_until(my_chunks < ahead ? my_chunks : ahead);
       }
-      mbar_wait(&full[slot], phase);
-      const float4* sl = s_state + static_cast<size_t>(slot) * kChunk;
-      float4 ya = live_a ? sl[t] : make_float4(0.f, 0.f, 0.f, 0.f);
-      float4 yb = live_b ? sl[t + kBlock] : make_float4(0.f, 0.f, 0.f, 0.f);
+      mbar_wait_u32(full_u32 + static_cast<uint32_t>(slot) * 8u, phase);
+      const uint32_t sl = state_u32 + static_cast<uint32_t>(slot) * (kChunk * 16u);
+      float4 ya = live_a ? lds128(sl) : make_float4(0.f, 0.f, 0.f, 0.f);
+      float4 yb = live_b ? lds128(sl + kBlock * 16u) : make_float4(0.f, 0.f, 0.f, 0.f);
       float aa = 0.f, ab = 0.f;
       if (act_tma) {
         const ActT* sa = s_act + static_cast<size_t>(slot) * kChunk;
@@ -138,7 +156,7 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
         if (live_b) ab = static_cast<float>(__ldg(act + i + kBlock));
       }
       __syncwarp();
-      if ((t & 31u) == 0) mbar_arrive(&empty[slot]);  // this warp's reads of the slot are done
+      if ((t & 31u) == 0) mbar_arrive_u32(empty_u32 + static_cast<uint32_t>(slot) * 8u);  // this warp's reads of the slot are done
       slot += kTmaGroups;
       while (slot >= n_slots) {
         slot -= n_slots;

@@ -25,9 +25,62 @@ __global__ void snapshot_tail_kernel(uint8_t* __restrict__ dst, const uint8_t* _
   if (j < bytes) dst[j] = src[j];
 }
 
+// Time-major rollout records [T, n] (one element per (step, env)) -> env-major [n, T]: every env's trajectory becomes
+// contiguous, which is the order of the reference's dataset files (zoo/util.py:33-93 appends whole episodes one
+// after another).  32 x 32 tiles through shared memory: reads coalesced along n, writes coalesced along T.
+// HBM-bound: 2 x bytes.
+template <typename E>
+__global__ void __launch_bounds__(kBlock) records_transpose_kernel(const E* __restrict__ in, E* __restrict__ out, int64_t T,
+                                                                   int64_t n, int64_t tiles_n, int64_t tiles) {
+  __shared__ E tile[32][33];
+  const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;  // 32 x 8
+  for (int64_t tl = blockIdx.x; tl < tiles; tl += gridDim.x) {
+    const int64_t t0 = (tl / tiles_n) * 32, i0 = (tl % tiles_n) * 32;
+#pragma unroll
+    for (int r = 0; r < 32; r += 8) {
+      const int64_t t = t0 + ly + r, i = i0 + lx;
+      if (t < T && i < n) tile[ly + r][lx] = in[t * n + i];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 32; r += 8) {
+      const int64_t i = i0 + ly + r, t = t0 + lx;
+      if (t < T && i < n) out[i * T + t] = tile[lx][ly + r];
+    }
+    __syncthreads();
+  }
+}
+
+template <typename E>
+inline void launch_records_transpose(const void* in, void* out, int64_t T, int64_t n, cudaStream_t s) {
+  const int64_t tiles_n = (n + 31) / 32, tiles = tiles_n * ((T + 31) / 32);
+  const int64_t cap = static_cast<int64_t>(kNumSMs) * 8;
+  const int grid = static_cast<int>(tiles < cap ? tiles : cap);
+  records_transpose_kernel<E><<<grid, kBlock, 0, s>>>(static_cast<const E*>(in), static_cast<E*>(out), T, n, tiles_n, tiles);
+}
+
 }  // namespace emei
 
 extern "C" {
+
+int emei_records_transpose(const void* in, void* out, int64_t horizon, int64_t n, int32_t elem_bytes, emei_stream_t stream) {
+  using namespace emei;
+  if (horizon < 0 || n < 0) return EMEI_ERR_BAD_SIZE;
+  if (elem_bytes != 1 && elem_bytes != 4 && elem_bytes != 8 && elem_bytes != 16) return EMEI_ERR_BAD_PARAM;
+  if (horizon == 0 || n == 0) return EMEI_OK;
+  EMEI_CHECK_PTR(in);
+  EMEI_CHECK_PTR(out);
+  if (((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & static_cast<uintptr_t>(elem_bytes - 1)) != 0)
+    return EMEI_ERR_MISALIGNED;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  switch (elem_bytes) {
+    case 1: launch_records_transpose<uint8_t>(in, out, horizon, n, s); break;
+    case 4: launch_records_transpose<uint32_t>(in, out, horizon, n, s); break;
+    case 8: launch_records_transpose<uint2>(in, out, horizon, n, s); break;
+    default: launch_records_transpose<uint4>(in, out, horizon, n, s); break;
+  }
+  return launch_status();
+}
 
 int emei_snapshot_copy(void* dst, const void* src, int64_t bytes, emei_stream_t stream) {
   using namespace emei;

@@ -236,6 +236,14 @@ int emei_init_charged_ball_f64(uint8_t* on_circle, double* circle, double* free_
  * unless bytes % 16 != 0 (byte tail handled). */
 int emei_snapshot_copy(void* dst, const void* src, int64_t bytes, emei_stream_t stream);
 
+/* ---- rollout records -> dataset order --------------------------------------------------------------
+ * The reference writes its offline datasets episode after episode (zoo/util.py:33-93,108-111: flat arrays
+ * observations, next_observations, actions, rewards, dones, timeouts).  The fused rollouts record time-major
+ * [horizon, n] arrays; this transposes one of them to env-major [n, horizon] (each env's trajectory, hence each
+ * of its episodes, contiguous).  elem_bytes: 1 (dones, timeouts, uint8 actions), 4 (rewards, float/int32 actions),
+ * 8 (int64/double actions), 16 (observation rows).  in/out aligned to elem_bytes. */
+int emei_records_transpose(const void* in, void* out, int64_t horizon, int64_t n, int32_t elem_bytes, emei_stream_t stream);
+
 /* ---- statistics --------------------------------------------------------------------------------- */
 int emei_stats_reset(double* stats, emei_stream_t stream); /* zero double[2] */
 

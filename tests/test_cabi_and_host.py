@@ -72,6 +72,71 @@ def test_argument_validation_codes():
     assert [lib.emei_family_action_dim(k) for k in (_lib.HOPPER, _lib.HALFCHEETAH, _lib.CARTPOLE_SWINGUP)] == [3, 6, 1]
 
 
+def test_rollout_and_transpose_validation_codes():
+    lib = _lib.lib
+    assert ctypes.sizeof(_lib.RolloutParams) == 6 * 4 + 4 * 8 + 2 * 8 + 8 * 8 + 2 * 8
+    p = _lib.CartPoleParams()
+    p.freq_rate, p.dt, p.variant, p.action_kind = 4, 0.02, _lib.CARTPOLE_SWINGUP, 3
+    r = _lib.RolloutParams()
+    r.horizon, r.random_policy = 8, 1
+    f = lib.emei_cartpole_rollout_f32
+    nul = [None] * 12
+    assert f(*nul, -1, ctypes.byref(p), ctypes.byref(r), None) == -4
+    assert f(*nul, 0, ctypes.byref(p), ctypes.byref(r), None) == 0       # empty batch: no-op
+    assert f(*nul, 16, ctypes.byref(p), None, None) == -1
+    assert f(*nul, 16, ctypes.byref(p), ctypes.byref(r), None) == -1     # null state
+    r.init_kind = 5
+    assert f(*nul, 16, ctypes.byref(p), ctypes.byref(r), None) == -6
+    r.init_kind, r.horizon = 0, 0
+    assert f(*nul, 16, ctypes.byref(p), ctypes.byref(r), None) == 0      # zero steps: no-op
+    c = _lib.ChargedBallParams()
+    c.gravity_acc, c.mass_ball, c.radius, c.charge, c.time_step, c.freq_rate, c.action_kind = 9.8, 1.0, 1.0, 10.0, 0.02, 1, 0
+    g = lib.emei_charged_ball_rollout_f32
+    r.horizon = 4
+    assert g(*([None] * 14), 16, ctypes.byref(c), ctypes.byref(r), None) == -1
+    c.radius = 0.0
+    assert g(*([None] * 14), 16, ctypes.byref(c), ctypes.byref(r), None) == -6
+    t = lib.emei_records_transpose
+    assert t(None, None, 4, -1, 4, None) == -4
+    assert t(None, None, 4, 8, 3, None) == -6          # element sizes: 1, 4, 8, 16
+    assert t(None, None, 0, 8, 4, None) == 0
+    assert t(None, None, 4, 8, 4, None) == -1
+
+
+def test_offline_dataset_files_roundtrip(tmp_path, monkeypatch):
+    """zoo/util.py:108-111 + core.py:61-81,109-128: flat files with the six keys, the reference's key checks, and
+    the cache layout DATASET_PATH/<env_name>/<env_params_name>/<file> behind dataset_names / get_dataset."""
+    from emei_b200 import offline
+
+    rng = np.random.default_rng(0)
+    n = 37
+    ds = dict(observations=rng.normal(size=(n, 4)).astype(np.float32), next_observations=rng.normal(size=(n, 4)).astype(np.float32),
+              actions=rng.integers(0, 2, n), rewards=rng.normal(size=n).astype(np.float32),
+              dones=(rng.random(n) < 0.1).astype(np.float32), timeouts=np.zeros(n, np.float32))
+    monkeypatch.setattr(offline, "DATASET_PATH", tmp_path)
+    env = E.make("CartPoleSwingUp-v0", freq_rate=2)
+    assert env.dataset_names == []
+    path = offline.save_dataset(ds, offline.dataset_path(env, "random.npz"))
+    assert path == tmp_path / "CartPoleSwingUp" / "freq_rate=2&integrator=euler&real_time_scale=0.02" / "random.npz"
+    assert env.dataset_names == ["random.npz"]
+    back = env.get_dataset("random.npz")
+    assert sorted(back) == sorted(ds) and all(np.array_equal(back[k], ds[k]) for k in ds)
+    with pytest.raises(FileNotFoundError):
+        env.get_dataset("expert.h5")
+    bad = dict(ds)
+    del bad["timeouts"]
+    with pytest.raises(AssertionError, match="missing key timeouts"):
+        offline.check_dataset(bad)
+    bad = dict(ds, rewards=ds["rewards"][:-1])
+    with pytest.raises(AssertionError):
+        offline.check_dataset(bad)
+    try:
+        import h5py  # noqa: F401
+    except ImportError:
+        with pytest.raises(ImportError):
+            offline.save_dataset(ds, tmp_path / "x.h5")
+
+
 def test_env_params_name(golden):
     """test/test_core.py:9-14."""
     env = EmeiEnv(env_params={"a": 3, "b": 5, "d": 0.33, "c": "c"})

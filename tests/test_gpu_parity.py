@@ -949,3 +949,46 @@ def test_step_kernel_large_batches_equal_scalar_rollout(env_id, cont, n):
     c.state = st
     obs2, rew2, done2, _, _ = c.step(act2)
     assert torch.equal(obs2, obs) and torch.equal(rew2, rew) and torch.equal(done2, done)
+
+
+# ================================================================================================
+# rollout records -> the reference's dataset order (zoo/util.py:33-93,108-111)
+# ================================================================================================
+@pytest.mark.parametrize("T,n", ((1, 1), (37, 1000), (64, 33), (5, 4097)))
+def test_records_transpose_bit_exact(T, n):
+    from emei_b200 import offline
+
+    g = torch.Generator(device="cuda")
+    g.manual_seed(T * 7919 + n)
+    stream = torch.cuda.current_stream().cuda_stream
+    for shape, dtype in (((T, n, 4), torch.float32), ((T, n), torch.float32), ((T, n), torch.uint8), ((T, n), torch.int64), ((T, n), torch.bool)):
+        x = torch.randint(0, 250, shape, device="cuda", generator=g).to(dtype)
+        y = offline._transpose(x, stream)
+        assert y.dtype == x.dtype and torch.equal(y, x.transpose(0, 1).contiguous())
+
+
+@pytest.mark.parametrize("env_id", ("CartPoleSwingUp-v0", "ContinuousChargedBallCentering-v0"))
+def test_collect_dataset_matches_reference_layout(env_id, tmp_path):
+    from emei_b200 import offline
+
+    n, total = 256, 256 * 90
+    env = E.make(env_id, num_envs=n, dtype=torch.float32)
+    env.max_episode_steps = 40
+    env._reseed(4)
+    samples, info = offline.collect_dataset(env, total)
+    N = samples["observations"].shape[0]
+    assert N == total and samples["observations"].shape == (N, 4) and samples["rewards"].shape == (N,)
+    assert samples["dones"].dtype == np.float32 and set(np.unique(samples["dones"])) <= {0.0, 1.0}
+    cont = env_id.startswith("Continuous")
+    assert samples["actions"].shape == ((N, 1) if cont else (N,))
+    # env-major: inside one env's trajectory consecutive samples chain unless an episode ended (zoo/util.py:73)
+    T = total // n
+    obs, nxt = samples["observations"].reshape(n, T, 4), samples["next_observations"].reshape(n, T, 4)
+    dones = samples["dones"].reshape(n, T).astype(bool)
+    chain = (nxt[:, :-1] == obs[:, 1:]).all(axis=2)
+    assert chain[~dones[:, :-1]].all() and not chain[dones[:, :-1]].all()
+    assert (samples["timeouts"] <= samples["dones"]).all() and samples["timeouts"].sum() > 0
+    assert info["total_episode_num"] == int(dones.sum()) and 1 <= info["avg_length"] <= 40
+    path = offline.save_dataset(samples, tmp_path / "random.npz")
+    back = offline.load_dataset(path, device=env.device)
+    assert all(torch.equal(back[k].cpu(), torch.as_tensor(samples[k])) for k in offline.KEYS)
