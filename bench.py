@@ -646,6 +646,15 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)", 1965.0
 
 
+def measured_traffic(workload):
+    """dram bytes per launch of the dominant kernel from the committed ncu --set full capture (profiles/traffic.json,
+    written by scripts/make_traffic_json.py); None when there is no capture for this workload."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(workload)
+    except Exception:
+        return None
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -785,6 +794,14 @@ def run_ours(args):
             "t_hbm_us": t_hbm * 1e6, "slower_bound": "math" if t_math > t_hbm else "hbm",
             "frac_of_slower_bound": max(t_math, t_hbm) / (kern_ms * 1e-3),
         }
+    tr = measured_traffic(args.workload)
+    if tr is not None:
+        roofline["traffic"] = tr["bytes_per_launch"]
+        roofline["traffic_source"] = f"{tr['source']}: dram__bytes_read.sum + dram__bytes_write.sum of {tr['kernel'][:60]}... per launch (ncu --set full, cold L2; writes may still sit in the 126 MB L2 when the launch ends)"
+        roofline["algorithmic_bytes_per_launch"] = wl.alg_bytes * wl.units
+        if not wl.use_graph and wl.bound == "hbm":  # kernels much larger than L2: the capture's DRAM bytes at this run's duration
+            roofline["dram_gbs_by_traffic"] = tr["bytes_per_launch"] / (kern_ms * 1e-3) / 1e9
+            roofline["dram_frac_by_traffic"] = roofline["dram_gbs_by_traffic"] / peak
     cfg = {"workload": wl.name}
     cfg.update(wl.config())
     cfg["launch"] = (f"K={K} steps captured in one CUDA graph (programmatic dependent launches), replayed once" if wl.use_graph
