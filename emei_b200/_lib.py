@@ -90,6 +90,15 @@ class ScoringParams(Structure):
     ]
 
 
+class I2PParams(Structure):
+    _fields_ = [
+        ("gravity", c_double), ("mass_cart", c_double), ("mass_pole0", c_double), ("mass_pole1", c_double),
+        ("length0", c_double), ("length1", c_double), ("gear", c_double), ("ctrl_low", c_double), ("ctrl_high", c_double),
+        ("x_left", c_double), ("x_right", c_double), ("dt", c_double),
+        ("freq_rate", c_int32), ("variant", c_int32), ("action_kind", c_int32),
+    ]
+
+
 class RolloutParams(Structure):
     _fields_ = [
         ("horizon", c_int32),
@@ -116,6 +125,7 @@ _PROTOTYPES = {
     # name: (restype, argtypes)
     "emei_cartpole_step": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int64, POINTER(CartPoleParams), _P]),
     "emei_charged_ball_step": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int64, POINTER(ChargedBallParams), _P]),
+    "emei_i2p_step": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int64, POINTER(I2PParams), _P]),
     "emei_reward_terminal": (c_int, [_P, _P, _P, _P, _P, _P, c_int64, POINTER(ScoringParams), _P]),
     "emei_sumsq": (c_int, [_P, c_int64, _P, _P, _P]),
     "emei_init_uniform": (c_int, [_P, c_int64, c_int32, c_double, c_double, c_int32, c_uint64, c_uint64, _P]),

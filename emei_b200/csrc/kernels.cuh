@@ -746,3 +746,5 @@ int init_charged_ball(uint8_t* on_circle, R* circle, R* free_state, int64_t n, d
 }
 
 }  // namespace emei
+
+#include "i2p.cuh"

@@ -245,6 +245,79 @@ class CartPoleEngine(RolloutMixin):
         self.has_state = True
 
 
+class I2PEngine:
+    """analytic inverted double pendulum (emei_i2p_step_*): state [B,6] ping-pong pair + observation buffers."""
+
+    def __init__(self, env, params: _lib.I2PParams):
+        self.env = env
+        self.params = params
+        self.n = env.num_envs
+        self._bufs = self._obs = self._out = None
+        self._cur = 0
+        self.has_state = False
+
+    def _alloc(self):
+        if self._bufs is None:
+            dev, dt = self.env.device, self.env.dtype
+            self._bufs = [torch.empty((self.n, 6), dtype=dt, device=dev) for _ in range(2)]
+            self._obs = [torch.empty((self.n, 6), dtype=dt, device=dev) for _ in range(2)]
+            self._out = StepOutputs(self.n, dt, dev)
+
+    @property
+    def state(self) -> Optional[torch.Tensor]:
+        return self._bufs[self._cur] if self.has_state else None
+
+    def set_state(self, state):
+        self._alloc()
+        s, _ = self.env._to_device(state, self.env.dtype)
+        if tuple(s.shape) != (self.n, 6):
+            raise ValueError(f"state must have shape {(self.n, 6)}, got {tuple(s.shape)}")
+        self._bufs[self._cur].copy_(s)
+        self.has_state = True
+
+    def step(self, action: torch.Tensor, copy_obs: bool):
+        env = self.env
+        self._alloc()
+        nxt = 1 - self._cur
+        src, dst = self._bufs[self._cur], self._bufs[nxt]
+        obs, reward, done = self._obs[nxt], self._out.reward[nxt], self._out.done[nxt]
+        if copy_obs:
+            obs, reward, done = torch.empty_like(obs), torch.empty_like(reward), torch.empty_like(done)
+        self.params.action_kind = _ACTION_KIND[action.dtype]
+        env._call(
+            "emei_i2p_step", src.data_ptr(), dst.data_ptr(), obs.data_ptr(), action.data_ptr(), reward.data_ptr(),
+            done.data_ptr(), env.stats.data_ptr(), self.n, ctypes.byref(self.params), env._stream(),
+        )
+        self._cur = nxt
+        return obs, reward, done.view(torch.bool)
+
+    def next_obs_stateless(self, obs: torch.Tensor, action: torch.Tensor):
+        """get_batch_next_obs: one dynamics step from caller-supplied STATES (the 6-d observation of this family
+        does not determine the state: inverted_double_pendulum.py:56-60 is not a bijection); engine untouched."""
+        b = obs.shape[0]
+        out, o2 = torch.empty_like(obs), torch.empty_like(obs)
+        r = torch.empty((b, 1), dtype=obs.dtype, device=obs.device)
+        d = torch.empty((b, 1), dtype=torch.uint8, device=obs.device)
+        self.params.action_kind = _ACTION_KIND[action.dtype]
+        self.env._call("emei_i2p_step", obs.data_ptr(), out.data_ptr(), o2.data_ptr(), action.data_ptr(), r.data_ptr(),
+                       d.data_ptr(), None, b, ctypes.byref(self.params), self.env._stream())
+        return o2
+
+    def snapshot(self):
+        src = self._bufs[self._cur]
+        snap = torch.empty_like(src)
+        with torch.cuda.device(self.env.device):
+            _lib.call("emei_snapshot_copy", snap.data_ptr(), src.data_ptr(), src.numel() * src.element_size(), self.env._stream())
+        return snap
+
+    def restore(self, snap: torch.Tensor):
+        self._alloc()
+        dst = self._bufs[self._cur]
+        with torch.cuda.device(self.env.device):
+            _lib.call("emei_snapshot_copy", dst.data_ptr(), snap.data_ptr(), snap.numel() * snap.element_size(), self.env._stream())
+        self.has_state = True
+
+
 class ChargedBallEngine(RolloutMixin):
     """charged ball (emei_charged_ball_step_*): three state arrays updated in place."""
 

@@ -143,6 +143,31 @@ int emei_cartpole_rollout_f32(float* state_io, int32_t* episode_step_io, float* 
                               uint8_t* rec_timeouts, double* stats, int64_t n, const emei_cartpole_params* p,
                               const emei_rollout_params* r, emei_stream_t stream);
 
+/* ---- analytic inverted double pendulum ----------------------------------------
+ * The reference's I2P accelerations are MuJoCo's (third-party mj_step); this is the reference's own Lagrangian
+ * model, classic_control/auxiliary/lagrange_eqs.py:12-60 cartpole(2) (cart + two thin rods, relative hinge angles,
+ * inertia 1/3 m l^2), with the complete potential energy (the script omits the height of pole 1's hinge for
+ * n >= 2, lagrange_eqs.py:45), the constants of assets/inverted_double_pendulum.xml:25,31,32,35,38,45 and the
+ * forward-Euler rule of mujoco_env.py:91-97. */
+typedef struct emei_i2p_params {
+  double gravity, mass_cart, mass_pole0, mass_pole1, length0, length1; /* lengths = half a pole (hinge -> COM) */
+  double gear, ctrl_low, ctrl_high;                                    /* force = gear * clamp(ctrl) (xml:45) */
+  double x_left, x_right;                                              /* slider range (xml:31) */
+  double dt;                                                           /* real_time_scale */
+  int32_t freq_rate;
+  int32_t variant;     /* EMEI_I2P_* : SwingUp variants flip pole 0 (inverted_double_pendulum.py:146-148,181-183) */
+  int32_t action_kind; /* EMEI_ACTION_* */
+} emei_i2p_params;
+
+/*   state_in/out [n,6] = [x, th0, th1, v, w0, w1] (qpos||qvel, angles unwrapped) ; obs_out [n,6] REQUIRED
+ *   (current_obs, inverted_double_pendulum.py:56-60, precedence quirk `(th + pi) % 2 * pi - pi` replicated) ;
+ *   action [n] ; reward [n], done [n] = get_batch_reward / get_batch_terminal of the variant on obs_out
+ *   (:84-90,114-122,150-157,185-196) ; stats nullable double[2].  Two launches: dynamics, then the scoring kernel. */
+int emei_i2p_step_f32(const float* state_in, float* state_out, float* obs_out, const void* action, float* reward,
+                      uint8_t* done, double* stats, int64_t n, const emei_i2p_params* p, emei_stream_t stream);
+int emei_i2p_step_f64(const double* state_in, double* state_out, double* obs_out, const void* action, double* reward,
+                      uint8_t* done, double* stats, int64_t n, const emei_i2p_params* p, emei_stream_t stream);
+
 /* ---- charged ball ----------------------------------------------------------------------------- */
 typedef struct emei_charged_ball_params {
   double gravity_acc, mass_ball, radius, charge, time_step; /* charged_ball.py:13-17 */

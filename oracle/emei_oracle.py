@@ -291,6 +291,118 @@ def transition_graph_power(g, num_obs, num_action, repeat_times):
 # =============================================================================================
 # inverted double pendulum reward / terminal (inverted_double_pendulum.py:84-196)
 # =============================================================================================
+@dataclass
+class I2PParams:
+    """Constants from assets/inverted_double_pendulum.xml: gravity (:25), slider range (:31), gear / ctrlrange (:45),
+    capsule geoms (:32 cart r=0.1 half-len 0.1; :35,:38 poles r=0.045, fromto length 0.6) at MuJoCo's default
+    density 1000 kg/m^3 (capsule volume = pi r^2 L + 4/3 pi r^3).  length = half a pole (hinge -> COM)."""
+
+    gravity: float = 9.81
+    gear: float = 500.0
+    ctrl_low: float = -1.0
+    ctrl_high: float = 1.0
+    length0: float = 0.3
+    length1: float = 0.3
+    x_left: float = -3.0
+    x_right: float = 3.0
+    mass_cart: float = 1000.0 * (math.pi * 0.1**2 * 0.2 + 4.0 / 3.0 * math.pi * 0.1**3)
+    mass_pole0: float = 1000.0 * (math.pi * 0.045**2 * 0.6 + 4.0 / 3.0 * math.pi * 0.045**3)
+    mass_pole1: float = 1000.0 * (math.pi * 0.045**2 * 0.6 + 4.0 / 3.0 * math.pi * 0.045**3)
+
+
+def i2p_accel(q, qd, force, swingup: bool, p: I2PParams, dtype=np.float64, script_literal=False, libm=False):
+    """Accelerations [x'', th0'', th1''] of the cart + two poles (relative hinge angles, as MuJoCo's qpos).
+
+    Lagrange equations of ``classic_control/auxiliary/lagrange_eqs.py:12-60`` ``cartpole(2)`` (thin-rod inertia
+    1/3 m l^2 about the COM, :37), written as ``A(q) a = b(q, qd, F)`` with the symmetric mass matrix solved by
+    LDL^T elimination in a fixed operation order (the CUDA kernel follows the same order):
+
+        A00 = M + m0 + m1          A01 = (m0 + 2 m1) l0 c0 + m1 l1 c01        A02 = m1 l1 c01
+        A11 = 4/3 m0 l0^2 + 4 m1 l0^2 + 4 m1 l0 l1 c1 + 4/3 m1 l1^2           A12 = 2 m1 l0 l1 c1 + 4/3 m1 l1^2
+        A22 = 4/3 m1 l1^2
+        b0 = F + (m0 + 2 m1) l0 s0 w0^2 + m1 l1 s01 (w0 + w1)^2
+        b1 = g l0 (m0 + 2 m1) s0 + g l1 m1 s01 + 2 l0 l1 m1 s1 w1 (2 w0 + w1)
+        b2 = l1 m1 (g s01 - 2 l0 s1 w0^2)
+
+    ``script_literal=True`` drops the ``2 m1`` of the gravity term of b1, which is what the reference script's
+    potential energy yields (it omits the height of pole 1's hinge, lagrange_eqs.py:45); see
+    oracle/gen_golden_i2p.py.  SwingUp models flip pole 0 (``body_quat[2] = [0,0,1,0]``,
+    inverted_double_pendulum.py:146-148,181-183): theta_0 = 0 hangs down, i.e. theta_0 + pi in the equations."""
+    T = np.dtype(dtype).type
+    q, qd = np.asarray(q, dtype=dtype), np.asarray(qd, dtype=dtype)
+    F = np.asarray(force, dtype=dtype).reshape(-1)
+    sign = T(-1.0) if swingup else T(1.0)
+    if libm:
+        import math as _m
+
+        sin = np.vectorize(_m.sin, otypes=[dtype])
+        cos = np.vectorize(_m.cos, otypes=[dtype])
+    else:
+        sin, cos = np.sin, np.cos
+    th0, th1, w0, w1 = q[:, 1], q[:, 2], qd[:, 1], qd[:, 2]
+    s0, c0 = sign * sin(th0), sign * cos(th0)
+    s1, c1 = sin(th1), cos(th1)
+    th01 = th0 + th1
+    s01, c01 = sign * sin(th01), sign * cos(th01)
+    M, m0, m1, l0, l1, g = (T(v) for v in (p.mass_cart, p.mass_pole0, p.mass_pole1, p.length0, p.length1, p.gravity))
+    k_a = (m0 + T(2) * m1) * l0          # (m0 + 2 m1) l0
+    k_b = m1 * l1                        # m1 l1
+    k_c = T(2) * m1 * l0 * l1            # 2 m1 l0 l1
+    k_d = T(4.0 / 3.0) * m1 * l1 * l1    # 4/3 m1 l1^2
+    k_e = T(4.0 / 3.0) * m0 * l0 * l0 + T(4) * m1 * l0 * l0 + k_d
+    k_g1 = g * l0 * ((m0 + T(2) * m1) if not script_literal else m0)
+    a00 = M + m0 + m1
+    a01 = k_a * c0 + k_b * c01
+    a02 = k_b * c01
+    a11 = k_e + T(2) * k_c * c1
+    a12 = k_c * c1 + k_d
+    a22 = k_d
+    ws = w0 + w1
+    b0 = F + k_a * s0 * (w0 * w0) + k_b * s01 * (ws * ws)
+    b1 = k_g1 * s0 + g * k_b * s01 + k_c * s1 * (w1 * (T(2) * w0 + w1))
+    b2 = k_b * (g * s01 - T(2) * l0 * s1 * (w0 * w0))
+    # LDL^T
+    l10 = a01 / a00
+    l20 = a02 / a00
+    d1 = a11 - l10 * a01
+    t12 = a12 - l10 * a02
+    l21 = t12 / d1
+    d2 = a22 - l20 * a02 - l21 * t12
+    y1 = b1 - l10 * b0
+    y2 = b2 - l20 * b0 - l21 * y1
+    z2 = y2 / d2
+    z1 = y1 / d1 - l21 * z2
+    z0 = b0 / a00 - l10 * z1 - l20 * z2
+    return np.stack([z0, z1, z2], axis=1)
+
+
+def i2p_wrap_obs(state):
+    """inverted_double_pendulum.py:56-60 ``current_obs``: ``state[1:3] = (state[1:3] + pi) % 2 * pi - pi`` -- the
+    precedence makes it ((theta + pi) mod 2) * pi - pi, not a wrap to [-pi, pi) (quirk ledger; replicated)."""
+    obs = np.array(state, copy=True)
+    obs[:, 1:3] = (obs[:, 1:3] + np.pi) % 2 * np.pi - np.pi
+    return obs
+
+
+def i2p_step(state, ctrl, h, freq_rate, swingup: bool, p: I2PParams, dtype=np.float64, libm=False):
+    """Analytic I2P step.  state [B,6] = [x, th0, th1, v, w0, w1] (qpos||qvel, mujoco_env.py:142-144), angles
+    unwrapped.  Per sub-step (mujoco_env.py:91-97, integrator="euler"): (q, v) <- (q + v h, v + a(q, v) h); force =
+    gear * clip(ctrl) (inverted_double_pendulum.xml:45; mj_step clamps ctrl to ctrlrange).  -> (new_state, obs)."""
+    T = np.dtype(dtype).type
+    y = np.array(state, dtype=dtype, copy=True)
+    c = np.clip(np.asarray(ctrl, dtype=dtype).reshape(-1), T(p.ctrl_low), T(p.ctrl_high))
+    force = T(p.gear) * c
+    h = T(h)
+    with np.errstate(all="ignore"):
+        for _ in range(int(freq_rate)):
+            acc = i2p_accel(y[:, :3], y[:, 3:], force, swingup, p, dtype=dtype, libm=libm)
+            q_new = y[:, :3] + y[:, 3:] * h
+            v_new = y[:, 3:] + acc * h
+            y[:, :3], y[:, 3:] = q_new, v_new
+        obs = i2p_wrap_obs(y)
+    return y, obs
+
+
 def i2p_reward(kind, obs):
     obs = np.asarray(obs)
     if kind.endswith("balancing"):

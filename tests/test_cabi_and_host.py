@@ -37,6 +37,7 @@ def test_struct_layouts_match_header():
     assert ctypes.sizeof(_lib.CartPoleParams) == 13 * 8 + 4 * 4
     assert ctypes.sizeof(_lib.ChargedBallParams) == 5 * 8 + 2 * 4
     assert ctypes.sizeof(_lib.ScoringParams) == 2 * 4 + 13 * 8
+    assert ctypes.sizeof(_lib.I2PParams) == 12 * 8 + 3 * 4 + 4  # padded to a multiple of 8
 
 
 def test_argument_validation_codes():
@@ -96,6 +97,16 @@ def test_rollout_and_transpose_validation_codes():
     assert g(*([None] * 14), 16, ctypes.byref(c), ctypes.byref(r), None) == -1
     c.radius = 0.0
     assert g(*([None] * 14), 16, ctypes.byref(c), ctypes.byref(r), None) == -6
+    q = _lib.I2PParams()
+    q.gravity, q.mass_cart, q.mass_pole0, q.mass_pole1, q.length0, q.length1, q.dt = 9.81, 10.0, 4.0, 4.0, 0.3, 0.3, 0.02
+    q.freq_rate, q.variant, q.action_kind = 1, _lib.I2P_BOUNDARY_SWINGUP, 3
+    h = lib.emei_i2p_step_f64
+    assert h(None, None, None, None, None, None, None, 0, ctypes.byref(q), None) == 0
+    assert h(None, None, None, None, None, None, None, 4, ctypes.byref(q), None) == -1
+    q.variant = _lib.HOPPER
+    assert h(None, None, None, None, None, None, None, 4, ctypes.byref(q), None) == -2
+    q.variant, q.length1 = _lib.I2P_REBOUND_BALANCING, 0.0
+    assert h(None, None, None, None, None, None, None, 4, ctypes.byref(q), None) == -6
     t = lib.emei_records_transpose
     assert t(None, None, 4, -1, 4, None) == -4
     assert t(None, None, 4, 8, 3, None) == -6          # element sizes: 1, 4, 8, 16

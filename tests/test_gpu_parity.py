@@ -992,3 +992,94 @@ def test_collect_dataset_matches_reference_layout(env_id, tmp_path):
     path = offline.save_dataset(samples, tmp_path / "random.npz")
     back = offline.load_dataset(path, device=env.device)
     assert all(torch.equal(back[k].cpu(), torch.as_tensor(samples[k])) for k in offline.KEYS)
+
+
+# ================================================================================================
+# analytic inverted double pendulum step
+# ================================================================================================
+I2P = {
+    "i2p_rebound_balancing": "ReboundInvertedDoublePendulumBalancing-v0",
+    "i2p_boundary_balancing": "BoundaryInvertedDoublePendulumBalancing-v0",
+    "i2p_rebound_swingup": "ReboundInvertedDoublePendulumSwingUp-v0",
+    "i2p_boundary_swingup": "BoundaryInvertedDoublePendulumSwingUp-v0",
+}
+
+
+def i2p_inputs(seed, n):
+    rng = np.random.default_rng(seed)
+    st = rng.uniform(-1, 1, size=(n, 6)) * np.array([2.9, np.pi, np.pi, 4.0, 8.0, 10.0])
+    st[: n // 8, 1:3] *= 20.0  # unwrapped angles
+    st[n // 8 : n // 4, 0] = np.sign(st[n // 8 : n // 4, 0]) * rng.uniform(2.95, 3.05, n // 4 - n // 8)  # the rail ends
+    st[n // 4 : n // 2, 1:3] *= 0.1  # near upright: the balancing variants' y threshold
+    act = rng.uniform(-1.3, 1.3, size=(n, 1)).astype(np.float32)  # beyond ctrlrange: clamped like mj_step
+    return st, act
+
+
+@pytest.mark.parametrize("kind", list(I2P))
+@pytest.mark.parametrize("fr", (1, 3))
+def test_i2p_step_f64_vs_oracle(kind, fr):
+    n = 4096
+    st, act = i2p_inputs(3001, n)
+    p = O.I2PParams()
+    ref_state, ref_obs = O.i2p_step(st, act.astype(np.float64), 0.02, fr, kind.endswith("swingup"), p, libm=True)
+    env = E.make(I2P[kind], freq_rate=fr, num_envs=n, dtype=torch.float64)
+    env.state = st
+    env.reset_stats()
+    obs, rew, done, trunc, info = env.step(act)
+    assert trunc is False and info == {}
+    assert close64(env.state.cpu().numpy(), ref_state, 1e-11)
+    o = obs.cpu().numpy()
+    # the observation's "(theta + pi) % 2 * pi - pi" jumps by 2 pi where (theta + pi) crosses an even integer:
+    # compare it from the engine's own state, and the state against the oracle
+    assert np.allclose(o, O.i2p_wrap_obs(env.state.cpu().numpy()), rtol=0, atol=1e-12)
+    assert close64(rew.cpu().numpy(), O.i2p_reward(kind, o), 1e-11)
+    ref_done = O.i2p_terminal(kind, o)
+    y = np.cos(o[:, 1]) + np.cos(o[:, 1] + o[:, 2])
+    near = (np.abs(np.abs(o[:, 0]) - 3.0) < 1e-9) | (np.abs(y - 1.5) < 1e-9) | (np.abs(y) < 1e-9)
+    assert np.array_equal(done.cpu().numpy()[~near], ref_done[~near])
+    assert 0 < ref_done.mean() < 1 or kind == "i2p_rebound_swingup"
+    rs, dc = env.read_stats()
+    assert dc == int(done.sum()) and abs(rs - float(rew.sum())) < 1e-6 * max(1.0, abs(rs))
+
+
+@pytest.mark.parametrize("kind", ("i2p_boundary_swingup", "i2p_rebound_balancing"))
+def test_i2p_step_f32_vs_oracle_identical_inputs(kind):
+    n = 4096
+    st, act = i2p_inputs(3002, n)
+    st[: n // 8, 1:3] /= 20.0  # float32 cannot hold angles of tens of radians to 1e-6
+    st32 = st.astype(np.float32)
+    p = O.I2PParams()
+    ref_state, _ = O.i2p_step(st32.astype(np.float64), act.astype(np.float64), 0.02, 1, kind.endswith("swingup"), p)
+    env = E.make(I2P[kind], num_envs=n, dtype=torch.float32)
+    env.state = st32
+    obs, rew, done, _, _ = env.step(act)
+    got = env.state.cpu().numpy()
+    # accelerations reach 1e3 rad/s^2 near the mass matrix's weak direction: allow the float32 evaluation error of
+    # a (relative 1e-5 of |a| h) on the velocity rows
+    acc = np.abs(ref_state[:, 3:] - st32[:, 3:].astype(np.float64))
+    tol = 1e-6 + 1e-5 * np.abs(ref_state)
+    tol[:, 3:] += 2e-5 * acc
+    assert (np.abs(got - ref_state) <= tol).all()
+    assert np.array_equal(obs.cpu().numpy()[:, [0, 3, 4, 5]], got[:, [0, 3, 4, 5]])
+    assert rew.shape == (n, 1) and done.dtype == torch.bool
+
+
+def test_i2p_reset_freeze_next_obs_and_graph():
+    env = E.make("BoundaryInvertedDoublePendulumSwingUp-v0", num_envs=2048, dtype=torch.float64)
+    obs, info = env.reset(seed=5)
+    assert obs.shape == (2048, 6) and info == {} and float(obs.abs().max()) < 0.05  # N(0, 5e-3) on all six
+    assert abs(float(obs.std()) - 5e-3) < 5e-4
+    a = torch.rand(2048, device=env.device, dtype=torch.float64) * 2 - 1
+    env.freeze()
+    snap = env.state.clone()
+    nxt = env.get_batch_next_obs(env.state, action=a)  # stateless: the env does not move
+    assert torch.equal(env.state, snap)
+    o1, _, _, _, _ = env.step(a)
+    assert torch.equal(o1, nxt)
+    env.step(a)
+    env.unfreeze()
+    assert torch.equal(env.state, snap) and env.frozen is False
+    g = env.get_transition_graph()
+    assert g.shape == (7, 6) and g[6].tolist() == [0, 0, 0, 1, 1, 1]
+    with pytest.raises(NotImplementedError):
+        E.make("BoundaryInvertedDoublePendulumSwingUp-v0", obs_noise_params=0.1)

@@ -175,3 +175,47 @@ def test_ip_dynamics_matches_lagrangian_closed_form():
     r1 = (M + m) * xa + m * l * (ta * np.cos(th) - om**2 * np.sin(th)) - F
     r2 = (4.0 / 3.0) * m * l**2 * ta + m * l * xa * np.cos(th) - m * g * l * np.sin(th)
     assert np.abs(r1).max() < 1e-9 and np.abs(r2).max() < 1e-9
+
+
+def test_i2p_accelerations_match_both_derivations(golden):
+    """oracle.i2p_accel (closed form, LDL^T in the kernel's operation order) against (a) the reference's own
+    lagrange_eqs.py cartpole(2) EXECUTED and solved numerically, (b) an independent sympy derivation with the
+    complete potential energy (oracle/gen_golden_i2p.py)."""
+    g = golden("i2p_dynamics")
+    p = O.I2PParams()
+    assert np.allclose(g["params"], [p.gravity, p.mass_cart, p.mass_pole0, p.mass_pole1, p.length0, p.length1], rtol=0, atol=0)
+    for literal, key in ((False, "acc_physical"), (True, "acc_script")):
+        a = O.i2p_accel(g["q"], g["qd"], g["force"], False, p, script_literal=literal)
+        assert np.all(np.abs(a - g[key]) <= 1e-11 * np.maximum(1.0, np.abs(g[key])))
+    # the script's omission is not a rounding matter
+    assert np.abs(g["acc_script"] - g["acc_physical"]).max() > 1.0
+    # SwingUp models: pole 0 flipped == theta_0 + pi
+    q2 = g["q"].copy()
+    q2[:, 1] += np.pi
+    assert np.allclose(O.i2p_accel(g["q"], g["qd"], g["force"], True, p), O.i2p_accel(q2, g["qd"], g["force"], False, p), rtol=0, atol=1e-9)
+
+
+def test_i2p_step_energy_and_obs_quirk():
+    p = O.I2PParams()
+    rng = np.random.default_rng(3)
+    st = rng.uniform(-1, 1, size=(64, 6)) * np.array([1.0, 3.0, 3.0, 1.0, 2.0, 2.0])
+    # free motion (no force): total energy drifts only at the forward-Euler rate when h shrinks
+    def energy(y):
+        x, t0, t1, v, w0, w1 = y.T
+        M, m0, m1, l0, l1, g = p.mass_cart, p.mass_pole0, p.mass_pole1, p.length0, p.length1, p.gravity
+        v0x, v0y = v + l0 * np.cos(t0) * w0, -l0 * np.sin(t0) * w0
+        v1x = v + 2 * l0 * np.cos(t0) * w0 + l1 * np.cos(t0 + t1) * (w0 + w1)
+        v1y = -2 * l0 * np.sin(t0) * w0 - l1 * np.sin(t0 + t1) * (w0 + w1)
+        T = 0.5 * M * v**2 + 0.5 * m0 * (v0x**2 + v0y**2) + 0.5 * m1 * (v1x**2 + v1y**2) + 0.5 * (m0 * l0**2 / 3) * w0**2 + 0.5 * (m1 * l1**2 / 3) * (w0 + w1) ** 2
+        V = m0 * g * l0 * np.cos(t0) + m1 * g * (2 * l0 * np.cos(t0) + l1 * np.cos(t0 + t1))
+        return T + V
+    e0 = energy(st)
+    drift = []
+    for fr in (100, 1000):
+        y, _ = O.i2p_step(st, np.zeros(64), 0.01 / fr, fr, False, p)
+        drift.append(np.abs(energy(y) - e0).max())
+    assert drift[1] < drift[0] / 5 and drift[1] < 1e-2  # first-order integrator of an energy-conserving system
+    y, obs = O.i2p_step(st, rng.uniform(-2, 2, 64), 0.02, 2, True, p)  # ctrl beyond +-1 is clamped
+    y2, _ = O.i2p_step(st, np.clip(rng.uniform(-2, 2, 0), -1, 1) if False else np.zeros(64), 0.02, 2, True, p)
+    assert np.array_equal(obs[:, [0, 3, 4, 5]], y[:, [0, 3, 4, 5]])
+    assert np.allclose(obs[:, 1:3], (y[:, 1:3] + np.pi) % 2 * np.pi - np.pi, rtol=0, atol=0)
