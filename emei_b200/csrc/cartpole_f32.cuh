@@ -56,24 +56,33 @@ __device__ __forceinline__ float load_action_f32(const void* __restrict__ action
     return static_cast<float>(__ldg(static_cast<const double*>(action) + i));
 }
 
-// One env step for the state in registers.  FR > 0: compile-time sub-step count (unrolled);
-// FR == 0: run-time k.freq_rate.  LIBM selects the guarded slow sincos (cold path).
+// One env step for the state in registers, scalar form (rollout kernel, small-batch kernel, the cold redo of
+// the packed kernel).  FR > 0: compile-time sub-step count (unrolled); FR == 0: run-time k.freq_rate.
 // flip = 0x80000000 for the inverted pendulum's swing-up models (pole hangs down at theta = 0).
-template <bool IP, int FR, bool LIBM>
-__device__ __forceinline__ float integrate(float4& y, float f_mt, uint32_t flip, const CartPoleF32Consts& k) {
-  const int fr = FR > 0 ? FR : k.freq_rate;
-  float th_max = fabsf(IP ? y.y : y.z);
-#pragma unroll
+//
+// integrate_fast: f32::cartpole_integrate (one sincos + angle addition).  Returns false when its guard trips
+// (|theta| > kSinCosSaneMax, a sub-step increment beyond pi/4, Inf): the caller then restores the state and calls
+// integrate_libm, which evaluates sincosf at every sub-step.  cos_cp = cos of the final cart-pole angle.
+template <bool IP, int FR>
+__device__ __forceinline__ bool integrate_fast(float4& y, float f_mt, uint32_t flip, const CartPoleF32Consts& k, float& cos_cp) {
+  f32::LaneMax<float> dmax;
+  const float th0 = fabsf(IP ? y.y : y.z);
+  if constexpr (!IP)
+    cos_cp = f32::cartpole_integrate<float, FR>(y.x, y.y, y.z, y.w, -f_mt, 0u, k.k, k.freq_rate, dmax);  // [x, x_dot, theta, theta_dot]
+  else
+    cos_cp = f32::cartpole_integrate<float, FR>(y.x, y.z, y.y, y.w, -f_mt, flip, k.k, k.freq_rate, dmax);  // [x, theta, v, omega]
+  return th0 <= f32::kSinCosSaneMax && dmax.m <= f32::kDeltaMax;
+}
+template <bool IP, int FR>
+__device__ __noinline__ float4 integrate_libm(float4 y, float f_mt, uint32_t flip, const f32::CartPoleK k, int freq_rate) {
+  const int fr = FR > 0 ? FR : freq_rate;
   for (int sub = 0; sub < fr; ++sub) {
-    if constexpr (!IP) {
-      f32::cartpole_substep<LIBM>(y.x, y.y, y.z, y.w, f_mt, 0u, k.k);  // [x, x_dot, theta, theta_dot]
-      th_max = fmaxf(th_max, fabsf(y.z));
-    } else {
-      f32::cartpole_substep<LIBM>(y.x, y.z, y.y, y.w, f_mt, flip, k.k);  // [x, theta, v, omega]
-      th_max = fmaxf(th_max, fabsf(y.y));
-    }
+    if constexpr (!IP)
+      f32::cartpole_substep<true>(y.x, y.y, y.z, y.w, f_mt, 0u, k);
+    else
+      f32::cartpole_substep<true>(y.x, y.z, y.y, y.w, f_mt, flip, k);
   }
-  return th_max;
+  return y;
 }
 
 __device__ __forceinline__ uint32_t ip_flip(bool ip, int variant) {
@@ -99,15 +108,16 @@ __device__ __forceinline__ float action_to_f_mt(float a, const CartPoleF32Consts
 }
 
 // reward, not-done flag and observation of one env after its step (cartpole.py:124-129,145-151;
-// inverted_pendulum.py:45-49,73-79,103-111,139-146,174-183).  cos_th = cos of the reward angle when the caller
-// already has it (packed evaluation), else computed here.
+// inverted_pendulum.py:45-49,73-79,103-111,139-146,174-183).  have_cos: cos_in = cos of the reward angle from
+// the integrator (cart-pole: theta; IP: the IP's own theta, i.e. the integrator's value with the flip undone);
+// otherwise (the env was redone with the libm path) it is computed here.
 template <bool IP>
-__device__ __forceinline__ void cartpole_outcome(const float4& y, bool sane, bool have_cos, float cos_in, const CartPoleF32Consts& k,
+__device__ __forceinline__ void cartpole_outcome(const float4& y, bool have_cos, float cos_in, const CartPoleF32Consts& k,
                                                  float& rew, bool& notdone, float4& obs) {
   obs = y;
   if constexpr (!IP) {
     if (k.variant == EMEI_CARTPOLE_SWINGUP) {
-      const float cth = have_cos ? cos_in : (sane ? f32::cos_core(y.z) : cosf(y.z));
+      const float cth = have_cos ? cos_in : cosf(y.z);
       rew = fmaf(cth, 0.5f, 0.5f);     // cartpole.py:149-151
       notdone = fabsf(y.x) < k.x_thr;  // cartpole.py:145-147
     } else {
@@ -139,6 +149,19 @@ __device__ __forceinline__ void cartpole_outcome(const float4& y, bool sane, boo
         break;
     }
   }
+}
+
+// the whole step of ONE env in scalar form: same bits as a lane of the packed step kernel
+template <bool IP, int FR>
+__device__ __forceinline__ void cartpole_step_one(float4& y, float f_mt, uint32_t flip, const CartPoleF32Consts& k, float& rew,
+                                                  bool& notdone, float4& obs) {
+  const float4 y0 = y;
+  float c;
+  const bool ok = integrate_fast<IP, FR>(y, f_mt, flip, k, c);
+  if (!ok) {
+    y = integrate_libm<IP, FR>(y0, f_mt, flip, k.k, k.freq_rate);
+  }
+  cartpole_outcome<IP>(y, ok, IP ? f32::u2f(f32::f2u(c) ^ flip) : c, k, rew, notdone, obs);
 }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }

@@ -14,6 +14,7 @@
 //
 // Chunk c = envs [512 c, 512 c + 512): thread t of a group owns envs 512 c + t and 512 c + 256 + t.
 #pragma once
+#include <type_traits>
 #include "cartpole_f32.cuh"
 
 namespace emei {
@@ -46,6 +47,26 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
   float4 v;
   asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
   return v;
+}
+template <class T>
+__device__ __forceinline__ T lds_as(uint32_t addr) {  // one element of the staged action chunk
+  if constexpr (sizeof(T) == 1) {
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return static_cast<T>(v);
+  } else if constexpr (sizeof(T) == 4) {
+    uint32_t v;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    T r;
+    memcpy(&r, &v, 4);
+    return r;
+  } else {
+    unsigned long long v;
+    asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v) : "r"(addr) : "memory");
+    T r;
+    memcpy(&r, &v, 8);
+    return r;
+  }
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -127,40 +148,40 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
   if (tid == 0) issue_until(my_chunks < static_cast<uint32_t>(n_slots) ? my_chunks : static_cast<uint32_t>(n_slots));
   {
     // ------------------------------------------------------------------ consumers: group g takes local chunks g, g+4, ...
+    // Everything that does not change from chunk to chunk is computed here once; the loop carries one running
+    // env index and the slot / phase pair.  The body is compiled twice: FULL (every chunk but possibly the last
+    // of the batch: no per-lane predicates) and the ragged tail.
     const uint32_t g = tid / kBlock, t = tid % kBlock;
     const uint32_t flip = ip_flip(IP, k.variant);
-    // 32-bit shared-window addresses, computed once (the generic-pointer forms re-derive the window base per chunk)
+    const bool recycling = my_chunks > static_cast<uint32_t>(n_slots);  // CTA-uniform: the ring is reused
+    // 32-bit shared-window addresses (the generic-pointer forms re-derive the window base per chunk)
     const uint32_t state_u32 = smem_u32(s_state) + t * 16u, full_u32 = smem_u32(full), empty_u32 = smem_u32(empty);
-    int slot = static_cast<int>(g) % n_slots;
+    const uint32_t act_u32 = smem_u32(s_act) + t * static_cast<uint32_t>(sizeof(ActT));
+    const uint32_t i_step = kTmaGroups * gridDim.x * kChunk;
+    uint32_t i = (blockIdx.x + g * gridDim.x) * kChunk + t;  // env A of this thread in the current chunk; env B = i + kBlock
+    uint32_t slot = g % static_cast<uint32_t>(n_slots);
     uint32_t phase = (g / static_cast<uint32_t>(n_slots)) & 1u;
-    for (uint32_t j = g; j < my_chunks; j += kTmaGroups) {
-      const uint32_t c = blockIdx.x + j * gridDim.x;
-      const uint32_t i = c * kChunk + t;  // env A; env B = i + kBlock
-      const bool live_a = i < n, live_b = i + kBlock < n;
-      const bool act_tma = action_via_tma && (n - c * kChunk >= kChunk);
-      if (tid == 0) {  // recycle drained slots: everything up to n_slots chunks ahead of the one consumed now
-        const uint32_t ahead = j + static_cast<uint32_t>(n_slots);
-        issue_until(my_chunks < ahead ? my_chunks : ahead);
-      }
-      mbar_wait_u32(full_u32 + static_cast<uint32_t>(slot) * 8u, phase);
-      const uint32_t sl = state_u32 + static_cast<uint32_t>(slot) * (kChunk * 16u);
+
+    auto body = [&](auto full_tag) {
+      constexpr bool FULL = decltype(full_tag)::value;
+      const bool live_a = FULL || i < n, live_b = FULL || i + kBlock < n;
+      const bool act_tma = FULL && action_via_tma;  // partial tail: consumers read their actions directly
+      mbar_wait_u32(full_u32 + slot * 8u, phase);
+      const uint32_t sl = state_u32 + slot * (kChunk * 16u);
       float4 ya = live_a ? lds128(sl) : make_float4(0.f, 0.f, 0.f, 0.f);
       float4 yb = live_b ? lds128(sl + kBlock * 16u) : make_float4(0.f, 0.f, 0.f, 0.f);
       float aa = 0.f, ab = 0.f;
       if (act_tma) {
-        const ActT* sa = s_act + static_cast<size_t>(slot) * kChunk;
-        aa = static_cast<float>(sa[t]);
-        ab = static_cast<float>(sa[t + kBlock]);
+        const uint32_t al = act_u32 + slot * (kChunk * static_cast<uint32_t>(sizeof(ActT)));
+        aa = static_cast<float>(lds_as<ActT>(al));
+        ab = static_cast<float>(lds_as<ActT>(al + kBlock * static_cast<uint32_t>(sizeof(ActT))));
       } else {
         if (live_a) aa = static_cast<float>(__ldg(act + i));
         if (live_b) ab = static_cast<float>(__ldg(act + i + kBlock));
       }
-      __syncwarp();
-      if ((t & 31u) == 0) mbar_arrive_u32(empty_u32 + static_cast<uint32_t>(slot) * 8u);  // this warp's reads of the slot are done
-      slot += kTmaGroups;
-      while (slot >= n_slots) {
-        slot -= n_slots;
-        phase ^= 1u;
+      if (recycling) {
+        __syncwarp();
+        if ((t & 31u) == 0) mbar_arrive_u32(empty_u32 + slot * 8u);  // this warp's reads of the slot are done
       }
 
       const float fa = action_to_f_mt<IP, AK>(aa, k), fb = action_to_f_mt<IP, AK>(ab, k);
@@ -174,16 +195,9 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
         V = f32::f2_pack(ya.z, yb.z);
       }
       const f2 nf = f32::f2_pack(-fa, -fb);
-      float tma = fabsf(IP ? ya.y : ya.z), tmb = fabsf(IP ? yb.y : yb.z);
-      const int fr = FR > 0 ? FR : k.freq_rate;
-#pragma unroll
-      for (int sub = 0; sub < fr; ++sub) {
-        f32::cartpole_substep2(X, V, TH, W, nf, flip, k.k);
-        float ta, tb;
-        f32::f2_unpack(TH, ta, tb);
-        tma = fmaxf(tma, fabsf(ta));
-        tmb = fmaxf(tmb, fabsf(tb));
-      }
+      const float th0a = fabsf(IP ? ya.y : ya.z), th0b = fabsf(IP ? yb.y : yb.z);
+      f32::LaneMax<f2> dmax;
+      const f2 C = f32::cartpole_integrate<f2, FR>(X, V, TH, W, nf, flip, k.k, k.freq_rate, dmax);
       float4 na, nb;
       {
         float t0, t1;
@@ -194,50 +208,61 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
         f32::f2_unpack(TH, t0, t1);
         if constexpr (!IP) { na.z = t0; nb.z = t1; } else { na.y = t0; nb.y = t1; }
       }
-      // the unguarded sincos is valid while |theta| stays below kSinCosSaneMax; otherwise (or NaN) redo that
-      // env from its stored state with the libm path.  Cold: float32 theta is meaningless there.
-      const bool sane_a = tma <= f32::kSinCosSaneMax, sane_b = tmb <= f32::kSinCosSaneMax;
-      bool have_cos = true;
-      if (!(sane_a && sane_b)) {
-        have_cos = false;
-        if (!sane_a && live_a) {
-          na = state_in[i];
-          integrate<IP, FR, true>(na, fa, flip, k);
-        }
-        if (!sane_b && live_b) {
-          nb = state_in[i + kBlock];
-          integrate<IP, FR, true>(nb, fb, flip, k);
-        }
+      // cos of the reward angle from the integrator (IP: undo the flip of the hanging models)
+      float ca, cb;
+      f32::f2_unpack(C, ca, cb);
+      if constexpr (IP) {
+        ca = f32::u2f(f32::f2u(ca) ^ flip);
+        cb = f32::u2f(f32::f2u(cb) ^ flip);
       }
-      // ---- reward angle cosine, packed (cart-pole swing-up: cos(theta); IP: cos(wrapped theta))
-      float ca = 0.f, cb = 0.f;
-      if (have_cos) {
-        if constexpr (!IP) {
-          if (k.variant == EMEI_CARTPOLE_SWINGUP) f32::f2_unpack(f32::cos_core(f32::f2_pack(na.z, nb.z)), ca, cb);
-        } else {
-          f32::f2_unpack(f32::cos_core(f32::f2_pack(wrap_pi_f32(na.y), wrap_pi_f32(nb.y))), ca, cb);
-        }
+      // the integrator's guard (f32math.cuh): otherwise (Inf, absurd angles or rates) redo that env from its
+      // stored state with the libm path.  Cold: float32 theta is meaningless there.
+      const bool ok_a = th0a <= f32::kSinCosSaneMax && dmax.a <= f32::kDeltaMax;
+      const bool ok_b = th0b <= f32::kSinCosSaneMax && dmax.b <= f32::kDeltaMax;
+      if (!(ok_a && ok_b)) {
+        if (!ok_a && live_a) na = integrate_libm<IP, FR>(state_in[i], fa, flip, k.k, k.freq_rate);
+        if (!ok_b && live_b) nb = integrate_libm<IP, FR>(state_in[i + kBlock], fb, flip, k.k, k.freq_rate);
       }
       float rew_a, rew_b;
       bool nd_a, nd_b;
       float4 oa, ob;
-      cartpole_outcome<IP>(na, sane_a, have_cos, ca, k, rew_a, nd_a, oa);
-      cartpole_outcome<IP>(nb, sane_b, have_cos, cb, k, rew_b, nd_b, ob);
+      cartpole_outcome<IP>(na, ok_a, ca, k, rew_a, nd_a, oa);
+      cartpole_outcome<IP>(nb, ok_b, cb, k, rew_b, nd_b, ob);
+      float4* so = state_out + i;
+      float* ro = reward + i;
+      uint8_t* dn = done + i;
       if (live_a) {
-        state_out[i] = na;
+        so[0] = na;
         if constexpr (HAS_OBS) obs_out[i] = oa;
-        reward[i] = rew_a;
-        done[i] = nd_a ? 0 : 1;
+        ro[0] = rew_a;
+        dn[0] = nd_a ? 0 : 1;
         r_acc += rew_a;
         d_cnt += nd_a ? 0u : 1u;
       }
       if (live_b) {
-        state_out[i + kBlock] = nb;
+        so[kBlock] = nb;
         if constexpr (HAS_OBS) obs_out[i + kBlock] = ob;
-        reward[i + kBlock] = rew_b;
-        done[i + kBlock] = nd_b ? 0 : 1;
+        ro[kBlock] = rew_b;
+        dn[kBlock] = nd_b ? 0 : 1;
         r_acc += rew_b;
         d_cnt += nd_b ? 0u : 1u;
+      }
+    };
+
+    for (uint32_t j = g; j < my_chunks; j += kTmaGroups) {
+      if (recycling && tid == 0) {  // refill drained slots: everything up to n_slots chunks ahead of the one consumed now
+        const uint32_t ahead = j + static_cast<uint32_t>(n_slots);
+        issue_until(my_chunks < ahead ? my_chunks : ahead);
+      }
+      if (i - t + kChunk <= n)
+        body(std::true_type{});
+      else
+        body(std::false_type{});
+      i += i_step;
+      slot += kTmaGroups;
+      if (slot >= static_cast<uint32_t>(n_slots)) {  // n_slots >= kTmaGroups: at most one wrap
+        slot -= static_cast<uint32_t>(n_slots);
+        phase ^= 1u;
       }
     }
   }
@@ -264,6 +289,37 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
       }
     }
   }
+}
+
+// Small batches (n < kSmallBatch; BASELINE configs[0] is 4096 envs): launch latency is the whole cost, so the
+// shortest dependency chain wins -- one env per thread, direct 128-bit loads, 128-thread CTAs spread over as many
+// SMs as the batch allows, no staging.  Scalar form of the same arithmetic (bit-identical to the packed kernel).
+constexpr int kSmallBlock = 128;
+constexpr int64_t kSmallBatch = 8192;
+
+template <bool IP, int AK, int FR, bool HAS_OBS>
+__global__ void __launch_bounds__(kSmallBlock)
+    cartpole_step_f32_small_kernel(const float4* __restrict__ state_in, float4* __restrict__ state_out,
+                                   float4* __restrict__ obs_out, const void* __restrict__ action,
+                                   float* __restrict__ reward, uint8_t* __restrict__ done, double* stats, uint32_t n,
+                                   const CartPoleF32Consts k) {
+  const uint32_t i = blockIdx.x * kSmallBlock + threadIdx.x;
+  float rew = 0.f;
+  bool notdone = true;
+  pdl_trigger();
+  pdl_wait();
+  if (i < n) {
+    float4 y = state_in[i];
+    const float f_mt = action_to_f_mt<IP, AK>(load_action_f32<AK>(action, i), k);
+    const uint32_t flip = ip_flip(IP, k.variant);
+    float4 obs;
+    cartpole_step_one<IP, FR>(y, f_mt, flip, k, rew, notdone, obs);
+    state_out[i] = y;
+    if constexpr (HAS_OBS) obs_out[i] = obs;
+    reward[i] = rew;
+    done[i] = notdone ? 0 : 1;
+  }
+  block_stats_accumulate_counts(stats, static_cast<double>(rew), notdone ? 0u : 1u);
 }
 
 // slots, dynamic shared memory bytes for an action element size
@@ -305,6 +361,30 @@ template <bool IP, int FR>
 inline void launch_cartpole_f32_tma(int ak, cudaStream_t s, const float* state_in, float* state_out, float* obs_out,
                                     const void* action, int action_bytes, float* reward, uint8_t* done, double* stats,
                                     int64_t n, const CartPoleF32Consts& k) {
+  if (n < kSmallBatch) {
+    const float4* in4 = reinterpret_cast<const float4*>(state_in);
+    float4* out4 = reinterpret_cast<float4*>(state_out);
+    float4* obs4 = reinterpret_cast<float4*>(obs_out);
+    const int grid = grid_for(n, kSmallBlock);
+    switch (ak) {
+#define EMEI_AK(A)                                                                                                     \
+  case A:                                                                                                              \
+    if (obs4 != nullptr)                                                                                               \
+      launch_pdl(cartpole_step_f32_small_kernel<IP, A, FR, true>, grid, kSmallBlock, s, in4, out4, obs4, action, reward, \
+                 done, stats, static_cast<uint32_t>(n), k);                                                            \
+    else                                                                                                               \
+      launch_pdl(cartpole_step_f32_small_kernel<IP, A, FR, false>, grid, kSmallBlock, s, in4, out4, obs4, action, reward, \
+                 done, stats, static_cast<uint32_t>(n), k);                                                            \
+    break;
+      EMEI_AK(EMEI_ACTION_DISCRETE_U8)
+      EMEI_AK(EMEI_ACTION_DISCRETE_I32)
+      EMEI_AK(EMEI_ACTION_DISCRETE_I64)
+      EMEI_AK(EMEI_ACTION_CONTINUOUS_F32)
+      EMEI_AK(EMEI_ACTION_CONTINUOUS_F64)
+#undef EMEI_AK
+    }
+    return;
+  }
   for (int64_t off = 0; off < n; off += kCartPoleMaxLaunch) {
     const int64_t m = n - off < kCartPoleMaxLaunch ? n - off : kCartPoleMaxLaunch;
     const int64_t chunks = (m + kChunk - 1) / kChunk;

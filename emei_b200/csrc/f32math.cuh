@@ -93,9 +93,11 @@ __host__ __device__ __forceinline__ float vfma(float a, float b, float c) { retu
 #if EMEI_F32_DEVICE
 __host__ __device__ __forceinline__ float vmul(float a, float b) { return __fmul_rn(a, b); }
 __host__ __device__ __forceinline__ float vadd(float a, float b) { return __fadd_rn(a, b); }
+__host__ __device__ __forceinline__ float vneg(float a) { return -a; }
 #else
 __host__ __device__ __forceinline__ float vmul(float a, float b) { return a * b; }
 __host__ __device__ __forceinline__ float vadd(float a, float b) { return a + b; }
+__host__ __device__ __forceinline__ float vneg(float a) { return -a; }
 #endif
 template <class V>
 struct Splat;
@@ -133,6 +135,14 @@ __device__ __forceinline__ f2 vadd(f2 a, f2 b) {
   f2 d;
   asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d.v) : "l"(a.v), "l"(b.v));
   return d;
+}
+// exact negation of both lanes; ptxas folds it into the operand modifier of the consuming FFMA2 (-R.F32x2).
+// (A packed subtraction is deliberately NOT offered: ptxas contracts mul.rn.f32x2 + sub.rn.f32x2 into one FFMA2,
+// which would differ from the scalar __fmul_rn / __fsub_rn form by one rounding.)
+__device__ __forceinline__ f2 vneg(f2 a) {
+  float lo, hi;
+  f2_unpack(a, lo, hi);
+  return f2_pack(-lo, -hi);
 }
 template <>
 struct Splat<f2> {
@@ -288,6 +298,61 @@ __host__ __device__ __forceinline__ void cartpole_euler(V& x, V& xd, V& th, V& w
   xd = vfma(nx_acc, vsplat<V>(-k.dt), xd);
   th = vfma(w, dt, th);
   w = vfma(th_acc, dt, w);
+}
+
+// ---------------------------------------------------------------------------------------------
+// One env step = freq_rate sub-steps with ONE full sincos.  The reference evaluates sin/cos of the angle
+// at every sub-step (cartpole.py:51-52); between sub-steps the angle moves by d = theta_dot * dt exactly
+// (base_control.py:164), so (sin, cos) of the next angle follow from the angle-addition formulas with
+// sin d, cos d from the [-pi/4, pi/4] kernels -- no range reduction and no quadrant fix-up (16 of the 47
+// instructions of a packed sub-step were integer quadrant logic; ncu showed the step kernel bound by
+// issue slots).  It also tracks the reference more closely for large angles: the reference's float64 angle
+// is theta0 + sum(d) without the float32 rounding of the stored theta, and so is the rotated (sin, cos).
+// The caller checks |theta0| <= kSinCosSaneMax and max |d| <= kDeltaMax (LaneMax) once per env step
+// and redoes the rare env that fails with the libm path (cartpole_substep<true>).
+// Returns cos of the FINAL cart-pole angle (the swing-up reward), flipped like the sub-step values.
+// ---------------------------------------------------------------------------------------------
+constexpr float kDeltaMax = 0.785398185253143310546875f;  // float32(pi/4): |theta_dot| <= 39 rad/s at dt = 0.02
+
+template <class V>
+struct LaneMax;
+template <>
+struct LaneMax<float> {
+  float m = 0.0f;
+  __host__ __device__ __forceinline__ void acc(float d) { m = fmaxf(m, fabsf(d)); }
+};
+#ifdef __CUDACC__
+template <>
+struct LaneMax<f2> {
+  float a = 0.0f, b = 0.0f;
+  __device__ __forceinline__ void acc(f2 d) {
+    float x, y;
+    f2_unpack(d, x, y);
+    a = fmaxf(a, fabsf(x));
+    b = fmaxf(b, fabsf(y));
+  }
+};
+#endif
+
+#pragma nv_exec_check_disable
+template <class V, int FR>
+__host__ __device__ __forceinline__ V cartpole_integrate(V& x, V& xd, V& th, V& w, V nf_mt, uint32_t flip, const CartPoleK& k,
+                                                         int fr_runtime, LaneMax<V>& dmax) {
+  V s, c;
+  sincos_core(th, &s, &c, flip);
+  const int fr = FR > 0 ? FR : fr_runtime;
+#pragma unroll
+  for (int sub = 0; sub < fr; ++sub) {
+    const V d = vmul(w, vsplat<V>(k.dt));  // this sub-step's angle increment (th = fma(w, dt, th) in cartpole_euler)
+    dmax.acc(d);
+    cartpole_euler<V>(x, xd, th, w, s, c, nf_mt, k);
+    const V d2 = vmul(d, d);
+    const V sd = sin_poly<V>(d, d2), cd = cos_poly<V>(d2);
+    const V s_next = vfma(s, cd, vmul(c, sd));
+    c = vfma(c, cd, vneg(vmul(s, sd)));
+    s = s_next;
+  }
+  return c;
 }
 
 // sub-step of the state (x, xd, th, w).  flip = 0x80000000 for the inverted pendulum's hanging models.

@@ -120,15 +120,8 @@ struct CartPoleDyn {
     const uint32_t flip = ip_flip(IP, k.variant);
     const float f_mt = action_to_f_mt<IP, AK>(a, k);
     float4 y = e.y;
-    const float4 y0 = y;
-    const float th_max = integrate<IP, FR, false>(y, f_mt, flip, k);
-    const bool sane = th_max <= f32::kSinCosSaneMax;
-    if (!sane) {
-      y = y0;
-      integrate<IP, FR, true>(y, f_mt, flip, k);
-    }
     bool notdone;
-    cartpole_outcome<IP>(y, sane, false, 0.f, k, rew, notdone, next_obs);
+    cartpole_step_one<IP, FR>(y, f_mt, flip, k, rew, notdone, next_obs);
     e.y = y;
     terminated = !notdone;
   }

@@ -51,6 +51,8 @@ int main(int argc, char** argv) {
   double worst[4] = {0, 0, 0, 0}, worst_sc = 0;
   double sum2[4] = {0,0,0,0};
   double worst_plain[4] = {0, 0, 0, 0};
+  double worst_sub[4] = {0, 0, 0, 0}, worst_cos = 0, worst_cos_sub = 0;
+  long n_fallback = 0;
   for (long i = 0; i < n; ++i) {
     float st[4] = {(float)(U(rng) * 4), (float)(U(rng) * 5), (float)(U(rng) * th_scale), (float)(U(rng) * w_scale)};
     float a = (float)U(rng);
@@ -59,8 +61,31 @@ int main(int argc, char** argv) {
     ref_step(y, (double)force, fr, dt);
     float x = st[0], xd = st[1], th = st[2], w = st[3];
     const float f_mt = force * k.inv_mt;
-    for (int j = 0; j < fr; ++j) emei::f32::cartpole_substep<false>(x, xd, th, w, f_mt, 0u, k);
+    // shipped path: one full sincos, angle-addition between sub-steps (libm per sub-step when the guard trips)
+    emei::f32::LaneMax<float> dmax;
+    const float cfin = emei::f32::cartpole_integrate<float, 0>(x, xd, th, w, -f_mt, 0u, k, fr, dmax);
+    float cos_rew = cfin;
+    if (!(fabsf(st[2]) <= emei::f32::kSinCosSaneMax && dmax.m <= emei::f32::kDeltaMax)) {
+      ++n_fallback;
+      x = st[0]; xd = st[1]; th = st[2]; w = st[3];
+      for (int j = 0; j < fr; ++j) emei::f32::cartpole_substep<true>(x, xd, th, w, f_mt, 0u, k);
+      cos_rew = cosf(th);
+    }
     float o[4] = {x, xd, th, w};
+    {
+      const double e = fabs((double)cos_rew - cos(y[2]));
+      if (e > worst_cos) worst_cos = e;
+    }
+    {  // previous generation: full sincos at every sub-step
+      float q[4] = {st[0], st[1], st[2], st[3]};
+      for (int j = 0; j < fr; ++j) emei::f32::cartpole_substep<false>(q[0], q[1], q[2], q[3], f_mt, 0u, k);
+      for (int j = 0; j < 4; ++j) {
+        double e = fabs((double)q[j] - y[j]) / (1e-6 + 1e-5 * fabs(y[j]));
+        if (e > worst_sub[j]) worst_sub[j] = e;
+      }
+      const double e = fabs((double)emei::f32::cos_fast(q[2]) - cos(y[2]));
+      if (e > worst_cos_sub) worst_cos_sub = e;
+    }
     for (int j = 0; j < 4; ++j) {
       double e = fabs((double)o[j] - y[j]) / (1e-6 + 1e-5 * fabs(y[j]));
       if (e > worst[j]) worst[j] = e;
@@ -82,6 +107,8 @@ int main(int argc, char** argv) {
   }
   printf("n=%ld fr=%d th_scale=%g w_scale=%g\n", n, fr, th_scale, w_scale);
   printf("worst envelope fraction  x=%.4f xd=%.4f th=%.4f w=%.4f\n", worst[0], worst[1], worst[2], worst[3]);
+  printf("sincos-per-sub-step      x=%.4f xd=%.4f th=%.4f w=%.4f\n", worst_sub[0], worst_sub[1], worst_sub[2], worst_sub[3]);
+  printf("worst |cos(final theta) - ref|: %.3e (angle addition)  %.3e (cos of the stored float32 theta)   libm fallbacks: %ld\n", worst_cos, worst_cos_sub, n_fallback);
   printf("plain-f32 worst fraction x=%.4f xd=%.4f th=%.4f w=%.4f\n", worst_plain[0], worst_plain[1], worst_plain[2], worst_plain[3]);
   printf("rms envelope fraction    x=%.4f xd=%.4f th=%.4f w=%.4f\n", sqrt(sum2[0]/n), sqrt(sum2[1]/n), sqrt(sum2[2]/n), sqrt(sum2[3]/n));
   printf("worst |sincos_fast - libm| over |x|<=%g: %.3e (float32 ulp(1)=1.19e-7)\n", 30 * th_scale, worst_sc);

@@ -6,7 +6,7 @@
 #include <cstdlib>
 #include <vector>
 #include "../../emei_b200/csrc/cartpole_tma.cuh"
-#include "cartpole_cpasync_variant.cuh"
+#include "cartpole_tma_prev.cuh"
 
 using namespace emei;
 #include <cstring>
@@ -32,8 +32,9 @@ stream_kernel(const float4* in, float4* out, const float* __restrict__ act, floa
   }
 }
 
-// compute only: the same per-env arithmetic on register-resident synthetic states, no HBM traffic
-template <int MINB, int FR>
+// compute only: the same per-env arithmetic on register-resident synthetic states, no HBM traffic.
+// OLD = full sincos at every sub-step (the first two generations); otherwise the shipped integrator (one sincos + angle addition)
+template <int MINB, int FR, bool OLD>
 __global__ void __launch_bounds__(kBlock, MINB)
 compute_kernel(float* out, uint32_t n, const CartPoleF32Consts k) {
   const uint32_t stride = gridDim.x * kBlock;
@@ -41,15 +42,23 @@ compute_kernel(float* out, uint32_t n, const CartPoleF32Consts k) {
   for (uint32_t i = blockIdx.x * kBlock + threadIdx.x; i < n; i += stride) {
     float4 y = make_float4(1e-6f * i, 0.5f, 2e-6f * i, -1.0f);
     const float f_mt = 1e-7f * i;
-    const float th_max = integrate<false, FR, false>(y, f_mt, 0u, k);
-    const float rew = fmaf(f32::cos_core(y.z), 0.5f, 0.5f);
-    acc += rew + y.x + y.y + y.w + th_max;
+    float c;
+    if (OLD) {
+#pragma unroll
+      for (int sub = 0; sub < FR; ++sub) f32::cartpole_substep<false>(y.x, y.y, y.z, y.w, f_mt, 0u, k.k);
+      c = f32::cos_core(y.z);
+    } else {
+      f32::LaneMax<float> dm;
+      c = f32::cartpole_integrate<float, FR>(y.x, y.y, y.z, y.w, -f_mt, 0u, k.k, FR, dm);
+      acc += dm.m;
+    }
+    acc += fmaf(c, 0.5f, 0.5f) + y.x + y.y + y.w;
   }
   if (acc == 12345.678f) out[0] = acc;
 }
 
 // compute only, packed f32x2: two envs per thread (the arithmetic of the shipped step kernel)
-template <int MINB, int FR>
+template <int MINB, int FR, bool OLD>
 __global__ void __launch_bounds__(kBlock, MINB)
 compute2_kernel(float* out, uint32_t n, const CartPoleF32Consts k) {
   using f32::f2;
@@ -58,71 +67,22 @@ compute2_kernel(float* out, uint32_t n, const CartPoleF32Consts k) {
   for (uint32_t i = blockIdx.x * kBlock * 2 + threadIdx.x; i < n; i += stride) {
     f2 X = f32::f2_pack(1e-6f * i, 2e-6f * i), V = f32::f2_pack(0.5f, 0.25f), TH = f32::f2_pack(2e-6f * i, 1e-6f * i), W = f32::f2_pack(-1.f, 1.f);
     const f2 nf = f32::f2_pack(1e-7f * i, -1e-7f * i);
+    f2 C;
+    if (OLD) {
 #pragma unroll
-    for (int sub = 0; sub < FR; ++sub) f32::cartpole_substep2(X, V, TH, W, nf, 0u, k.k);
+      for (int sub = 0; sub < FR; ++sub) f32::cartpole_substep2(X, V, TH, W, nf, 0u, k.k);
+      C = f32::cos_core(TH);
+    } else {
+      f32::LaneMax<f2> dm;
+      C = f32::cartpole_integrate<f2, FR>(X, V, TH, W, nf, 0u, k.k, FR, dm);
+      acc += dm.a + dm.b;
+    }
     float a, b, c, d;
-    f32::f2_unpack(f32::cos_core(TH), a, b);
+    f32::f2_unpack(C, a, b);
     f32::f2_unpack(vadd(vadd(X, V), W), c, d);
     acc += a + b + c + d;
   }
   if (acc == 12345.678f) out[0] = acc;
-}
-
-// EXPERIMENT: two envs per thread per iteration (two independent dependency chains interleaved by
-// the compiler), cp.async ring of S stages x 2 envs.
-template <int MINB, int S>
-__global__ void __launch_bounds__(kBlock, MINB)
-cartpole_ilp2_kernel(const float4* state_in, float4* state_out, const float* __restrict__ act, float* __restrict__ reward,
-                     uint8_t* __restrict__ done, double* stats, uint32_t n, const CartPoleF32Consts k) {
-  __shared__ float4 s_state[S][2][kBlock];
-  __shared__ float s_act[S][2][kBlock];
-  const uint32_t tid = threadIdx.x;
-  const uint32_t half = gridDim.x * kBlock;   // env B of a pair sits `half` after env A
-  const uint32_t stride = 2 * half;
-  uint32_t i = blockIdx.x * kBlock + tid;
-  float r_acc = 0.f; unsigned d_cnt = 0;
-  auto stage_in = [&](int slot, uint32_t idx) {
-#pragma unroll
-    for (int e = 0; e < 2; ++e) {
-      const uint32_t j = idx + e * half;
-      if (j < n) { cp_async<16>(&s_state[slot][e][tid], state_in + j); cp_async<4>(&s_act[slot][e][tid], act + j); }
-    }
-    cp_async_commit();
-  };
-  pdl_trigger(); pdl_wait();
-#pragma unroll
-  for (int d = 0; d < S; ++d) stage_in(d, i + d * stride);
-  int slot = 0;
-  while (i < n) {
-    cp_async_wait<S - 1>();
-    float4 y[2]; float f_mt[2]; float th_max[2];
-#pragma unroll
-    for (int e = 0; e < 2; ++e) { y[e] = s_state[slot][e][tid]; f_mt[e] = (k.force_mag * s_act[slot][e][tid]) * k.k.inv_mt; th_max[e] = 0.f; }
-#pragma unroll
-    for (int sub = 0; sub < 4; ++sub) {
-#pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        f32::cartpole_substep<false>(y[e].x, y[e].y, y[e].z, y[e].w, f_mt[e], 0u, k.k);
-        th_max[e] = fmaxf(th_max[e], fabsf(y[e].z));
-      }
-    }
-    stage_in(slot, i + S * stride);
-    slot = slot + 1 == S ? 0 : slot + 1;
-#pragma unroll
-    for (int e = 0; e < 2; ++e) {
-      const uint32_t j = i + e * half;
-      if (j < n) {
-        if (!(th_max[e] <= f32::kSinCosSaneMax)) { y[e] = state_in[j]; integrate<false, 4, true>(y[e], f_mt[e], 1.0f, k); }
-        state_out[j] = y[e];
-        const float rew = fmaf(f32::cos_fast(y[e].z), 0.5f, 0.5f);
-        const unsigned d = fabsf(y[e].x) < k.x_thr ? 0u : 1u;
-        reward[j] = rew; done[j] = (uint8_t)d; r_acc += rew; d_cnt += d;
-      }
-    }
-    i += stride;
-  }
-  cp_async_wait<0>();
-  block_stats_accumulate_counts(stats, (double)r_acc, d_cnt);
 }
 
 struct Ring {
@@ -152,30 +112,7 @@ float time_graph(F launch, int K, cudaStream_t s, int reps = 5) {
   return best * 1e3f / K;  // us per launch
 }
 
-template <int MINB, int FR, bool PDL, int S = 4, int DBG = 0>
-void run_cartpole(const char* name, Ring& R, uint32_t n, int K, cudaStream_t s, int grid_override = 0) {
-  SKIP(name);
-  emei_cartpole_params p = {};
-  p.gravity = 9.8; p.mass_pole = 0.1; p.total_mass = 1.1; p.length = 0.5; p.pole_mass_length = 0.05; p.force_mag = 10.0;
-  p.x_threshold = 5.0; p.theta_threshold = 0.2; p.dt = 0.02; p.freq_rate = 4; p.variant = EMEI_CARTPOLE_SWINGUP;
-  p.action_kind = EMEI_ACTION_CONTINUOUS_F32;
-  CartPoleF32Consts k = make_cartpole_f32_consts(p);
-  int grid = grid_override ? grid_override : persistent_grid(n, 2 * kBlock, MINB);
-  double* stats; CK(cudaMalloc(&stats, 16)); CK(cudaMemset(stats, 0, 16));
-  const int ring = (int)R.in.size();
-  auto launch = [&](int i) {
-    int j = i % ring;
-    auto kern = cartpole_step_f32_kernel<false, EMEI_ACTION_CONTINUOUS_F32, FR, MINB, false, S, DBG>;
-    if (PDL) launch_pdl(kern, grid, kBlock, s, (const float4*)R.in[j], (float4*)R.out[j], (float4*)nullptr, (const void*)R.act[j], R.rew[j], R.done[j], stats, n, k);
-    else kern<<<grid, kBlock, 0, s>>>((const float4*)R.in[j], (float4*)R.out[j], nullptr, R.act[j], R.rew[j], R.done[j], stats, n, k);
-  };
-  float us = time_graph(launch, K, s);
-  CK(cudaGetLastError());
-  printf("%-44s grid=%5d  %7.2f us/launch  %6.1f Genv-steps/s  %6.0f GB/s (41 B/env)\n", name, grid, us, n / us * 1e-3, 41.0 * n / us * 1e-3);
-  cudaFree(stats);
-}
-
-template <int FR>
+template <int FR, bool PREV = false>
 void run_tma(const char* name, Ring& R, uint32_t n, int K, cudaStream_t s, int slots_cap = 0) {
   SKIP(name);
   emei_cartpole_params p = {};
@@ -190,7 +127,8 @@ void run_tma(const char* name, Ring& R, uint32_t n, int K, cudaStream_t s, int s
   if (slots_cap && n_slots > slots_cap) { n_slots = slots_cap; smem = (size_t)n_slots * kChunk * 20 + 2 * n_slots * 8 + (kTmaThreads / 32) * 12 + 16; }
   double* stats; CK(cudaMalloc(&stats, 16)); CK(cudaMemset(stats, 0, 16));
   const int ring = (int)R.in.size();
-  auto kern = cartpole_step_f32_tma_kernel<false, EMEI_ACTION_CONTINUOUS_F32, FR, false>;
+  auto kern = PREV ? cartpole_step_f32_tma_prev_kernel<false, EMEI_ACTION_CONTINUOUS_F32, FR, false>
+                   : cartpole_step_f32_tma_kernel<false, EMEI_ACTION_CONTINUOUS_F32, FR, false>;
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   auto launch = [&](int i) {
     int j = i % ring;
@@ -202,27 +140,7 @@ void run_tma(const char* name, Ring& R, uint32_t n, int K, cudaStream_t s, int s
   cudaFree(stats);
 }
 
-template <int MINB, int S>
-void run_ilp2(const char* name, Ring& R, uint32_t n, int K, cudaStream_t s) {
-  SKIP(name);
-  emei_cartpole_params p = {};
-  p.gravity = 9.8; p.mass_pole = 0.1; p.total_mass = 1.1; p.length = 0.5; p.pole_mass_length = 0.05; p.force_mag = 10.0;
-  p.x_threshold = 5.0; p.theta_threshold = 0.2; p.dt = 0.02; p.freq_rate = 4; p.variant = EMEI_CARTPOLE_SWINGUP;
-  CartPoleF32Consts k = make_cartpole_f32_consts(p);
-  int grid = persistent_grid((n + 1) / 2, kBlock, MINB);
-  double* stats; CK(cudaMalloc(&stats, 16)); CK(cudaMemset(stats, 0, 16));
-  const int ring = (int)R.in.size();
-  auto launch = [&](int i) {
-    int j = i % ring;
-    launch_pdl(cartpole_ilp2_kernel<MINB, S>, grid, kBlock, s, (const float4*)R.in[j], (float4*)R.out[j], (const float*)R.act[j], R.rew[j], R.done[j], stats, n, k);
-  };
-  float us = time_graph(launch, K, s);
-  CK(cudaGetLastError());
-  printf("%-44s grid=%5d  %7.2f us/launch  %6.1f Genv-steps/s  %6.0f GB/s (41 B/env)\n", name, grid, us, n / us * 1e-3, 41.0 * n / us * 1e-3);
-  cudaFree(stats);
-}
-
-template <int MINB, int FR>
+template <int MINB, int FR, bool OLD>
 void run_compute(const char* name, Ring& R, uint32_t n, int K, cudaStream_t s) {
   SKIP(name);
   emei_cartpole_params p = {};
@@ -230,13 +148,13 @@ void run_compute(const char* name, Ring& R, uint32_t n, int K, cudaStream_t s) {
   p.x_threshold = 5.0; p.theta_threshold = 0.2; p.dt = 0.02; p.freq_rate = 4; p.variant = EMEI_CARTPOLE_SWINGUP;
   CartPoleF32Consts k = make_cartpole_f32_consts(p);
   int grid = persistent_grid(n, kBlock, MINB);
-  auto launch = [&](int i) { compute_kernel<MINB, FR><<<grid, kBlock, 0, s>>>(R.rew[0], n, k); };
+  auto launch = [&](int i) { compute_kernel<MINB, FR, OLD><<<grid, kBlock, 0, s>>>(R.rew[0], n, k); };
   float us = time_graph(launch, K, s);
   CK(cudaGetLastError());
   printf("%-44s grid=%5d  %7.2f us/launch\n", name, grid, us);
 }
 
-template <int MINB, int FR>
+template <int MINB, int FR, bool OLD>
 void run_compute2(const char* name, Ring& R, uint32_t n, int K, cudaStream_t s) {
   SKIP(name);
   emei_cartpole_params p = {};
@@ -244,7 +162,7 @@ void run_compute2(const char* name, Ring& R, uint32_t n, int K, cudaStream_t s) 
   p.x_threshold = 5.0; p.theta_threshold = 0.2; p.dt = 0.02; p.freq_rate = 4; p.variant = EMEI_CARTPOLE_SWINGUP;
   CartPoleF32Consts k = make_cartpole_f32_consts(p);
   int grid = persistent_grid(n, 2 * kBlock, MINB);
-  auto launch = [&](int i) { compute2_kernel<MINB, FR><<<grid, kBlock, 0, s>>>(R.rew[0], n, k); };
+  auto launch = [&](int i) { compute2_kernel<MINB, FR, OLD><<<grid, kBlock, 0, s>>>(R.rew[0], n, k); };
   float us = time_graph(launch, K, s);
   CK(cudaGetLastError());
   printf("%-44s grid=%5d  %7.2f us/launch\n", name, grid, us);
@@ -286,24 +204,14 @@ int main(int argc, char** argv) {
   }
   printf("n=%u ring=%d K=%d\n", n, ring, K);
   run_stream<8, true>("stream minb8 pdl", R, n, K, s);
-  run_compute<4, 4>("compute-only scalar fr4 minb4", R, n, K, s);
-  run_compute2<2, 4>("compute-only packed fr4 minb2", R, n, K, s);
-  run_compute2<3, 4>("compute-only packed fr4 minb3", R, n, K, s);
-  run_compute2<4, 4>("compute-only packed fr4 minb4", R, n, K, s);
-  run_tma<4>("TMA packed fr4", R, n, K, s);
+  run_compute<4, 4, true>("compute-only scalar fr4 minb4 sincos/sub-step", R, n, K, s);
+  run_compute<4, 4, false>("compute-only scalar fr4 minb4 angle-addition", R, n, K, s);
+  run_compute2<4, 4, true>("compute-only packed fr4 minb4 sincos/sub-step", R, n, K, s);
+  run_compute2<4, 4, false>("compute-only packed fr4 minb4 angle-addition", R, n, K, s);
+  run_tma<4, true>("TMA packed fr4, previous loop structure", R, n, K, s);
+  run_tma<4>("TMA packed fr4 (shipped)", R, n, K, s);
   run_tma<4>("TMA packed fr4 slots<=8", R, n, K, s, 8);
-  run_tma<4>("TMA packed fr4 slots<=4", R, n, K, s, 4);
   run_tma<0>("TMA packed fr-runtime", R, n, K, s);
-  run_cartpole<2, 4, true, 4>("cartpole packed fr4 minb2 S4", R, n, K, s);
-  run_cartpole<2, 4, true, 2>("cartpole packed fr4 minb2 S2", R, n, K, s);
-  run_cartpole<3, 4, true, 4>("cartpole packed fr4 minb3 S4", R, n, K, s);
-  run_cartpole<3, 4, true, 3>("cartpole packed fr4 minb3 S3", R, n, K, s);
-  run_cartpole<3, 4, true, 2>("cartpole packed fr4 minb3 S2", R, n, K, s);
-  run_cartpole<4, 4, true, 2>("cartpole packed fr4 minb4 S2", R, n, K, s);
-  run_cartpole<4, 4, true, 3>("cartpole packed fr4 minb4 S3", R, n, K, s);
-  run_cartpole<3, 4, true, 3, 1>("cartpole packed fr4 minb3 S3 NO-STORE", R, n, K, s);
-  run_cartpole<3, 4, true, 3, 2>("cartpole packed fr4 minb3 S3 NO-LOAD", R, n, K, s);
-  run_cartpole<3, 0, true, 2>("cartpole packed fr-runtime minb3 S2", R, n, K, s);
-  run_cartpole<4, 0, true, 2>("cartpole packed fr-runtime minb4 S2", R, n, K, s);
+  run_tma<1>("TMA packed fr1", R, n, K, s);
   return 0;
 }
