@@ -99,6 +99,10 @@ class I2PParams(Structure):
     ]
 
 
+class NoiseParams(Structure):
+    _fields_ = [("sigma", c_double * 6), ("seed", c_uint64), ("env_offset", c_uint64), ("step", c_uint64)]
+
+
 class RolloutParams(Structure):
     _fields_ = [
         ("horizon", c_int32),
@@ -126,6 +130,8 @@ _PROTOTYPES = {
     "emei_cartpole_step": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int64, POINTER(CartPoleParams), _P]),
     "emei_charged_ball_step": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int64, POINTER(ChargedBallParams), _P]),
     "emei_i2p_step": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int64, POINTER(I2PParams), _P]),
+    "emei_ip_step_noisy": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int64, POINTER(CartPoleParams), POINTER(NoiseParams), _P]),
+    "emei_i2p_step_noisy": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int64, POINTER(I2PParams), POINTER(NoiseParams), _P]),
     "emei_reward_terminal": (c_int, [_P, _P, _P, _P, _P, _P, c_int64, POINTER(ScoringParams), _P]),
     "emei_sumsq": (c_int, [_P, c_int64, _P, _P, _P]),
     "emei_init_uniform": (c_int, [_P, c_int64, c_int32, c_double, c_double, c_int32, c_uint64, c_uint64, _P]),

@@ -213,6 +213,8 @@ class EmeiEnv(Freezable):
         Returns a dict with those records (if any) and ``stats``: device double[6] = [sum of rewards,
         #terminated, #truncated, #episodes finished, sum of finished returns, sum of finished lengths];
         ``rollout_info(stats)`` turns it into the reference's avg_reward / avg_length / total_episode_num."""
+        if getattr(self, "_obs_noise_on", lambda: False)():
+            raise NotImplementedError("obs_noise_params != 0 is implemented for step() only (emei_ip_step_noisy / emei_i2p_step_noisy)")
         eng = getattr(self, "_ensure_engine", lambda: self._engine)()
         if eng is None or not hasattr(eng, "rollout"):
             raise NotImplementedError(f"{type(self).__name__} has no fused rollout kernel")
@@ -257,6 +259,8 @@ class EmeiEnv(Freezable):
         staging buffers (valid until the next ``step_host``)."""
         from .engine import HostStaging
 
+        if getattr(self, "_obs_noise_on", lambda: False)():
+            raise NotImplementedError("obs_noise_params != 0 is implemented for step() only")
         if getattr(self, "_staging", None) is None:
             self._staging = HostStaging(self)
         return self._staging.step(action)

@@ -51,7 +51,7 @@ inline I2PConsts<R> make_i2p_consts(const emei_i2p_params& p) {
 template <typename R>
 __global__ void __launch_bounds__(kBlock)
     i2p_step_kernel(const R* __restrict__ state_in, R* __restrict__ state_out, R* __restrict__ obs_out,
-                    const void* __restrict__ action, int64_t n, const I2PConsts<R> k) {
+                    const void* __restrict__ action, int64_t n, const I2PConsts<R> k, const NoiseConsts z) {
   const int64_t stride = static_cast<int64_t>(gridDim.x) * kBlock;
   const R sign = k.swingup ? R(-1) : R(1);
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * kBlock + threadIdx.x; i < n; i += stride) {
@@ -92,6 +92,8 @@ __global__ void __launch_bounds__(kBlock)
       const R q0 = y[0] + y[3] * k.dt, q1 = y[1] + y[4] * k.dt, q2 = y[2] + y[5] * k.dt;
       const R v0 = y[3] + z0 * k.dt, v1 = y[4] + z1 * k.dt, v2 = y[5] + z2 * k.dt;
       y[0] = q0, y[1] = q1, y[2] = q2, y[3] = v0, y[4] = v1, y[5] = v2;
+      if (z.on)  // mujoco_env.py:98-104: Gaussian state noise after every sub-step
+        add_state_noise<R, 6>(y, z, z.env_offset + static_cast<unsigned long long>(i), z.substep0 + static_cast<unsigned long long>(sub));
     }
 #pragma unroll
     for (int j = 0; j < 6; ++j) state_out[6 * i + j] = y[j];
@@ -105,7 +107,7 @@ __global__ void __launch_bounds__(kBlock)
 // (included at the end of kernels.cuh: reward_terminal<R>() is defined above)
 template <typename R>
 int i2p_step(const R* state_in, R* state_out, R* obs_out, const void* action, R* reward, uint8_t* done, double* stats,
-             int64_t n, const emei_i2p_params* p, emei_stream_t stream) {
+             int64_t n, const emei_i2p_params* p, emei_stream_t stream, const emei_noise_params* noise = nullptr) {
   if (n < 0) return EMEI_ERR_BAD_SIZE;
   EMEI_CHECK_PTR(p);
   if (p->variant < EMEI_I2P_REBOUND_BALANCING || p->variant > EMEI_I2P_BOUNDARY_SWINGUP) return EMEI_ERR_BAD_VARIANT;
@@ -113,6 +115,9 @@ int i2p_step(const R* state_in, R* state_out, R* obs_out, const void* action, R*
   if (p->freq_rate < 1 || !(p->dt > 0.0) || !(p->mass_cart > 0.0) || !(p->mass_pole0 > 0.0) || !(p->mass_pole1 > 0.0) ||
       !(p->length0 > 0.0) || !(p->length1 > 0.0))
     return EMEI_ERR_BAD_PARAM;
+  if (noise != nullptr)
+    for (int j = 0; j < 6; ++j)
+      if (!(noise->sigma[j] >= 0.0)) return EMEI_ERR_BAD_PARAM;
   if (n == 0) return EMEI_OK;
   EMEI_CHECK_PTR(state_in);
   EMEI_CHECK_PTR(state_out);
@@ -122,7 +127,8 @@ int i2p_step(const R* state_in, R* state_out, R* obs_out, const void* action, R*
   EMEI_CHECK_PTR(done);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const I2PConsts<R> k = make_i2p_consts<R>(*p);
-  i2p_step_kernel<R><<<resident_grid(i2p_step_kernel<R>, n), kBlock, 0, s>>>(state_in, state_out, obs_out, action, n, k);
+  i2p_step_kernel<R><<<resident_grid(i2p_step_kernel<R>, n), kBlock, 0, s>>>(state_in, state_out, obs_out, action, n, k,
+                                                                             make_noise_consts(noise, p->freq_rate));
   const int rc = launch_status();
   if (rc != EMEI_OK) return rc;
   emei_scoring_params sp = {};

@@ -64,11 +64,54 @@ __device__ __forceinline__ double euler_cp(double y, double d, const CartPoleCon
   return y + static_cast<double>(__fmul_rn(static_cast<float>(d), k.dt32));
 }
 
+// ---------------------------------------------------------------------------------------------
+// Per-sub-step Gaussian state noise ("obs_noise_params": mujoco_env.py:98-104 adds
+// additive_gaussian_noise(qpos, qvel) to the simulator state after EVERY sub-step; :197-249 draws one
+// N(0, sigma_pos) / N(0, sigma_vel) per hinge/slide joint coordinate).  The reference's stream is numpy's
+// global Mersenne Twister; here coordinates 2*pr, 2*pr+1 of env e at global sub-step g are the Box-Muller
+// pair of Philox block (g * 4 + pr) keyed by (seed, e) -- same arithmetic as init_gaussian_kernel
+// (mirror: oracle/philox.py obs_noise).  on == 0: no noise, no cost beyond one uniform branch.
+// ---------------------------------------------------------------------------------------------
+constexpr uint32_t kPurposeObsNoise = 6;
+struct NoiseConsts {
+  double sigma[6];
+  unsigned long long seed, env_offset, substep0;  // substep0 = step * freq_rate: global index of this call's first sub-step
+  int on;
+};
+inline NoiseConsts make_noise_consts(const emei_noise_params* z, int freq_rate) {
+  NoiseConsts c = {};
+  if (z != nullptr) {
+    for (int j = 0; j < 6; ++j) c.sigma[j] = z->sigma[j];
+    c.seed = z->seed;
+    c.env_offset = z->env_offset;
+    c.substep0 = z->step * static_cast<unsigned long long>(freq_rate);
+    c.on = 1;
+  }
+  return c;
+}
+// y[c] += sigma[c] * N(0,1) for c < DIM (DIM even)
+template <typename R, int DIM>
+__device__ __forceinline__ void add_state_noise(R (&y)[DIM], const NoiseConsts& z, unsigned long long env, unsigned long long g) {
+#pragma unroll
+  for (int pr = 0; pr < DIM / 2; ++pr) {
+    const unsigned long long blk = g * 4ull + static_cast<unsigned long long>(pr);
+    uint32_t w[4];
+    Philox::generate(z.seed, env, static_cast<uint32_t>(blk), kPurposeObsNoise | (static_cast<uint32_t>(blk >> 32) << 8), w);
+    const double u1 = 1.0 - u01_from_bits(w[0], w[1]);
+    const double u2 = u01_from_bits(w[2], w[3]);
+    const double rad = sqrt(-2.0 * log(u1));
+    double sn, cs;
+    sincospi(2.0 * u2, &sn, &cs);
+    y[2 * pr] = static_cast<R>(__dadd_rn(static_cast<double>(y[2 * pr]), __dmul_rn(z.sigma[2 * pr], __dmul_rn(rad, cs))));
+    y[2 * pr + 1] = static_cast<R>(__dadd_rn(static_cast<double>(y[2 * pr + 1]), __dmul_rn(z.sigma[2 * pr + 1], __dmul_rn(rad, sn))));
+  }
+}
+
 template <typename R, bool IP>
 __global__ void __launch_bounds__(kBlock)
     cartpole_step_kernel(const R* state_in, R* state_out, R* obs_out, const void* __restrict__ action,
                          R* __restrict__ reward, uint8_t* __restrict__ done, double* stats, int64_t n,
-                         const CartPoleConsts<R> k) {
+                         const CartPoleConsts<R> k, const NoiseConsts z) {
   // persistent grid-stride loop; reward / done partials stay in registers and are reduced once per
   // thread (a per-env shuffle reduction makes streaming kernels MIO-bound, profiles/r01_ncu_full_c4)
   const int64_t stride = static_cast<int64_t>(gridDim.x) * kBlock;
@@ -115,6 +158,11 @@ __global__ void __launch_bounds__(kBlock)
         const R nx = y.x + y.z * k.dt, nth = y.y + y.w * k.dt;
         const R nv = y.z + x_acc * k.dt, nw = y.w + th_acc * k.dt;
         y.x = nx, y.y = nth, y.z = nv, y.w = nw;
+        if (z.on) {  // mujoco_env.py:98-104
+          R q[4] = {y.x, y.y, y.z, y.w};
+          add_state_noise<R, 4>(q, z, z.env_offset + static_cast<unsigned long long>(i), z.substep0 + static_cast<unsigned long long>(sub));
+          y.x = q[0], y.y = q[1], y.z = q[2], y.w = q[3];
+        }
       }
       y.store(state_out + 4 * i);
       // observation: theta wrapped, inverted_pendulum.py:45-49
@@ -156,13 +204,19 @@ __global__ void __launch_bounds__(kBlock)
 
 template <typename R>
 int cartpole_step(const R* state_in, R* state_out, R* obs_out, const void* action, R* reward, uint8_t* done,
-                  double* stats, int64_t n, const emei_cartpole_params* p, emei_stream_t stream) {
+                  double* stats, int64_t n, const emei_cartpole_params* p, emei_stream_t stream,
+                  const emei_noise_params* noise = nullptr) {
   if (n < 0) return EMEI_ERR_BAD_SIZE;
   EMEI_CHECK_PTR(p);
   if (p->variant < EMEI_CARTPOLE_BALANCING || p->variant > EMEI_IP_BOUNDARY_SWINGUP) return EMEI_ERR_BAD_VARIANT;
   if (p->action_kind < EMEI_ACTION_DISCRETE_U8 || p->action_kind > EMEI_ACTION_CONTINUOUS_F64)
     return EMEI_ERR_BAD_ACTION_KIND;
   if (p->freq_rate < 1 || !(p->dt > 0.0)) return EMEI_ERR_BAD_PARAM;
+  if (noise != nullptr) {  // the noisy step exists for the MuJoCo-shell family only (mujoco_env.py:98-104)
+    if (p->variant < EMEI_IP_REBOUND_BALANCING) return EMEI_ERR_BAD_VARIANT;
+    for (int j = 0; j < 4; ++j)
+      if (!(noise->sigma[j] >= 0.0)) return EMEI_ERR_BAD_PARAM;
+  }
   if (n == 0) return EMEI_OK;
   EMEI_CHECK_PTR(state_in);
   EMEI_CHECK_PTR(state_out);
@@ -175,17 +229,20 @@ int cartpole_step(const R* state_in, R* state_out, R* obs_out, const void* actio
   cudaStream_t s = static_cast<cudaStream_t>(stream);
 #ifdef EMEI_HAVE_CARTPOLE_F32
   if constexpr (sizeof(R) == 4) {  // lean float32 kernel: TMA-staged, packed f32x2 (cartpole_tma.cuh)
-    cartpole_step_f32_tma_dispatch(state_in, state_out, obs_out, action, reward, done, stats, n, *p, s);
-    return launch_status();
+    if (noise == nullptr) {        // (the noisy step takes the generic kernel below: Philox + double Box-Muller dominate it)
+      cartpole_step_f32_tma_dispatch(state_in, state_out, obs_out, action, reward, done, stats, n, *p, s);
+      return launch_status();
+    }
   }
 #endif
   const CartPoleConsts<R> k = make_cartpole_consts<R>(*p);
+  const NoiseConsts z = make_noise_consts(noise, p->freq_rate);
   if (p->variant <= EMEI_CARTPOLE_SWINGUP)
     cartpole_step_kernel<R, false><<<resident_grid(cartpole_step_kernel<R, false>, n), kBlock, 0, s>>>(
-        state_in, state_out, obs_out, action, reward, done, stats, n, k);
+        state_in, state_out, obs_out, action, reward, done, stats, n, k, z);
   else
     cartpole_step_kernel<R, true><<<resident_grid(cartpole_step_kernel<R, true>, n), kBlock, 0, s>>>(
-        state_in, state_out, obs_out, action, reward, done, stats, n, k);
+        state_in, state_out, obs_out, action, reward, done, stats, n, k, z);
   return launch_status();
 }
 

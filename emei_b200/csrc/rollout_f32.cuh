@@ -31,18 +31,26 @@ struct RolloutConsts {
   float act_low, act_high;
 };
 
-// same arithmetic as init_uniform_kernel / init_gaussian_kernel (kernels.cuh), one env row
+constexpr uint32_t kPurposeRolloutReset = 5;
+
+// In-rollout reset sample of one env row.
+// Uniform family (cartpole.py:131-132,153-156: U(low, high) per coordinate, + pi on the swing-up angle): the lean
+// float32 sampler of the rollout kernels -- ONE Philox block per reset, coordinate c = fma(high - low, u_c, low)
+// with u_c the top 24 bits of word c.  A reset is a divergent branch that a third of all warp-steps take under
+// the random policy, so its length is paid by the whole warp: the 53-bit double construction of the init kernels
+// (two blocks, four double conversions) cost ~360 warp instructions per event, this one ~110
+// (mirror: oracle/rollout_oracle.py reset_sample_uniform).
+// Gaussian family (mujoco_env.py:137-140): the arithmetic of init_gaussian_kernel (kernels.cuh).
 static __device__ __noinline__ float4 rollout_init_state(const RolloutConsts& r, unsigned long long env, unsigned long long seed) {
   float v[4];
   if (r.init_kind == 0) {
+    uint32_t w[4];
+    Philox::generate(seed, env, 0u, kPurposeRolloutReset, w);
+    const float lo = static_cast<float>(r.init_low), span = static_cast<float>(r.init_high) - lo;
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
-      uint32_t w[4];
-      Philox::generate(seed, env, static_cast<uint32_t>(c >> 1), 1u /*kPurposeUniform*/, w);
-      const double u = (c & 1) ? u01_from_bits(w[2], w[3]) : u01_from_bits(w[0], w[1]);
-      double x = __dadd_rn(r.init_low, __dmul_rn(r.init_high - r.init_low, u));
-      if (c == r.init_pi_column) x = __dadd_rn(x, 3.141592653589793238462643383279502884);
-      v[c] = static_cast<float>(x);
+      v[c] = fmaf(span, static_cast<float>(w[c] >> 8) * (1.0f / 16777216.0f), lo);
+      if (c == r.init_pi_column) v[c] = static_cast<float>(static_cast<double>(v[c]) + 3.141592653589793238462643383279502884);
     }
   } else {
 #pragma unroll

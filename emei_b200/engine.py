@@ -162,7 +162,7 @@ class CartPoleEngine(RolloutMixin):
         self.has_state = True
         self.new_episodes(reseed=False)
 
-    def step(self, action: torch.Tensor, copy_obs: bool):
+    def step(self, action: torch.Tensor, copy_obs: bool, noise: Optional[_lib.NoiseParams] = None):
         env = self.env
         self._alloc()
         src, dst = self._bufs[self._cur], self._bufs[1 - self._cur]
@@ -176,11 +176,12 @@ class CartPoleEngine(RolloutMixin):
         if copy_obs:
             reward, done = torch.empty_like(reward), torch.empty_like(done)
         self.params.action_kind = _ACTION_KIND[action.dtype]
-        env._call(
-            "emei_cartpole_step",
-            src.data_ptr(), dst.data_ptr(), obs.data_ptr() if obs is not None else None, action.data_ptr(),
-            reward.data_ptr(), done.data_ptr(), env.stats.data_ptr(), self.n, ctypes.byref(self.params), env._stream(),
-        )
+        ptrs = (src.data_ptr(), dst.data_ptr(), obs.data_ptr() if obs is not None else None, action.data_ptr(),
+                reward.data_ptr(), done.data_ptr(), env.stats.data_ptr(), self.n, ctypes.byref(self.params))
+        if noise is None:
+            env._call("emei_cartpole_step", *ptrs, env._stream())
+        else:  # obs_noise_params (mujoco_env.py:98-104): Gaussian state noise after every sub-step
+            env._call("emei_ip_step_noisy", *ptrs, ctypes.byref(noise), env._stream())
         self._cur = nxt
         return (obs if obs is not None else dst), reward, done.view(torch.bool)
 
@@ -275,7 +276,7 @@ class I2PEngine:
         self._bufs[self._cur].copy_(s)
         self.has_state = True
 
-    def step(self, action: torch.Tensor, copy_obs: bool):
+    def step(self, action: torch.Tensor, copy_obs: bool, noise: Optional[_lib.NoiseParams] = None):
         env = self.env
         self._alloc()
         nxt = 1 - self._cur
@@ -284,10 +285,12 @@ class I2PEngine:
         if copy_obs:
             obs, reward, done = torch.empty_like(obs), torch.empty_like(reward), torch.empty_like(done)
         self.params.action_kind = _ACTION_KIND[action.dtype]
-        env._call(
-            "emei_i2p_step", src.data_ptr(), dst.data_ptr(), obs.data_ptr(), action.data_ptr(), reward.data_ptr(),
-            done.data_ptr(), env.stats.data_ptr(), self.n, ctypes.byref(self.params), env._stream(),
-        )
+        ptrs = (src.data_ptr(), dst.data_ptr(), obs.data_ptr(), action.data_ptr(), reward.data_ptr(), done.data_ptr(),
+                env.stats.data_ptr(), self.n, ctypes.byref(self.params))
+        if noise is None:
+            env._call("emei_i2p_step", *ptrs, env._stream(), launches=2)
+        else:
+            env._call("emei_i2p_step_noisy", *ptrs, ctypes.byref(noise), env._stream(), launches=2)
         self._cur = nxt
         return obs, reward, done.view(torch.bool)
 

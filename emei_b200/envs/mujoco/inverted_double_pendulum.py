@@ -28,8 +28,6 @@ class BaseInvertedDoublePendulumEnv(EmeiMujocoEnv):
 
     def __init__(self, freq_rate: int = 1, real_time_scale: float = 0.02, integrator="euler",
                  init_noise_params=5e-3, obs_noise_params=0.0, **kwargs):
-        if obs_noise_params != 0:
-            raise NotImplementedError("obs_noise_params != 0 (mujoco_env.py:98-104) is a SURVEY 8(f) 'next' row")
         EmeiMujocoEnv.__init__(
             self, observation_dim=6, freq_rate=freq_rate, real_time_scale=real_time_scale, integrator=integrator,
             init_noise_params=init_noise_params, obs_noise_params=obs_noise_params, **kwargs,
@@ -99,13 +97,14 @@ class BaseInvertedDoublePendulumEnv(EmeiMujocoEnv):
         if self.integrator != "euler":
             raise NotImplementedError("the analytic inverted double pendulum implements integrator='euler' (mujoco_env.py:94-97)")
         self._reseed(seed)
+        self._noise_step = 0
         self.state = self._sample_init_obs(self.num_envs)  # reset_model: mujoco_env.py:130-135 (returns qpos||qvel)
         return self.state.clone(), {}
 
     def step(self, action):
         assert self.state is not None, "Call reset before using step method."
         a = normalise_action(self, action, True)
-        obs, reward, terminal = self._engine.step(a, self.copy_outputs)
+        obs, reward, terminal = self._engine.step(a, self.copy_outputs, noise=self._next_obs_noise())
         return obs, reward, terminal, False, {}
 
     def get_batch_next_obs(self, obs, pre_obs=None, action=None, state=None, pre_state=None):

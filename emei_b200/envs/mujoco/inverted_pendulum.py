@@ -32,8 +32,6 @@ class BaseInvertedPendulumEnv(EmeiMujocoEnv):
 
     def __init__(self, freq_rate: int = 1, real_time_scale: float = 0.02, integrator="euler",
                  init_noise_params=5e-3, obs_noise_params=0.0, **kwargs):
-        if obs_noise_params != 0:
-            raise NotImplementedError("obs_noise_params != 0 (mujoco_env.py:98-104) is a SURVEY 8(f) 'next' row")
         EmeiMujocoEnv.__init__(
             self, observation_dim=4, freq_rate=freq_rate, real_time_scale=real_time_scale, integrator=integrator,
             init_noise_params=init_noise_params, obs_noise_params=obs_noise_params, **kwargs,
@@ -107,6 +105,7 @@ class BaseInvertedPendulumEnv(EmeiMujocoEnv):
         if self.integrator != "euler":
             raise NotImplementedError("the analytic inverted pendulum implements integrator='euler' (mujoco_env.py:94-97)")
         self._reseed(seed)
+        self._noise_step = 0
         self.state = self._sample_init_obs(self.num_envs)  # reset_model: mujoco_env.py:130-135
         self._engine.new_episodes(reseed=True)
         return self.state.clone(), {}
@@ -114,7 +113,7 @@ class BaseInvertedPendulumEnv(EmeiMujocoEnv):
     def step(self, action):
         assert self.state is not None, "Call reset before using step method."
         a = normalise_action(self, action, True)
-        obs, reward, terminal = self._engine.step(a, self.copy_outputs)
+        obs, reward, terminal = self._engine.step(a, self.copy_outputs, noise=self._next_obs_noise())
         return obs, reward, terminal, False, {}
 
     def get_batch_next_obs(self, obs, pre_obs=None, action=None, state=None, pre_state=None):

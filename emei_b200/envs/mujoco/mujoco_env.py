@@ -14,6 +14,9 @@ Reference quirks (SURVEY.md appendix A + DESIGN.md):
     returns ``(obs[:, :nq], obs[:, nq:])``.
   * the noise uses the process-global ``np.random`` (ignores the env seed); here it is a Philox
     stream keyed by ``reset(seed=)``.
+  * ``obs_noise_params`` is, despite its name, STATE noise: after every sub-step the simulator state is
+    overwritten with ``additive_gaussian_noise(qpos, qvel)`` (:98-104).  Implemented for the analytic
+    pendulums (``emei_ip_step_noisy_*`` / ``emei_i2p_step_noisy_*``), same per-coordinate intent as above.
 """
 import ctypes
 from typing import Dict, Optional, Tuple, Union
@@ -72,6 +75,7 @@ class EmeiMujocoEnv(EmeiEnv):
         self.nq = self.nv = nq
         self.init_qpos = np.array(qpos0, dtype=np.float64)
         self.init_qvel = np.zeros(nq, dtype=np.float64)
+        self._noise_step = 0
         self.observation_space = spaces.Box(-np.inf, np.inf, shape=(observation_dim,), dtype=np.float64)
         self.action_space = spaces.Box(ctrl[0], ctrl[1], shape=(nu,), dtype=np.float32)
 
@@ -93,6 +97,27 @@ class EmeiMujocoEnv(EmeiEnv):
         else:
             sp[:], sv[:] = noise_params, noise_params
         return sp, sv
+
+    # ---- per-sub-step state noise (obs_noise_params, mujoco_env.py:98-104) -------------------------
+    def _obs_noise_on(self) -> bool:
+        sp, sv = self._noise_sigmas(self.obs_noise_params)
+        return bool(np.any(sp != 0) or np.any(sv != 0))
+
+    def _next_obs_noise(self) -> Optional[_lib.NoiseParams]:
+        """NoiseParams of the NEXT step call (None when obs_noise_params is zero): per-coordinate sigmas
+        (scalar / (pos, vel) / {jnt_id: (pos, vel)} forms of mujoco_env.py:217-227), a Philox key derived from
+        ``reset(seed=)`` and the env-step counter, which ``reset`` zeroes."""
+        if not self._obs_noise_on():
+            return None
+        sp, sv = self._noise_sigmas(self.obs_noise_params)
+        z = _lib.NoiseParams()
+        for j, v in enumerate(np.concatenate([sp, sv])):
+            z.sigma[j] = float(v)
+        z.seed = (self._seed * 0xA24BAED4963EE407 + 0x9FB21C651E98DF25) & 0xFFFFFFFFFFFFFFFF
+        z.env_offset = self.env_offset
+        z.step = self._noise_step
+        self._noise_step += 1
+        return z
 
     def get_batch_init_state(self, batch_size):
         """-> (pos [B,nq], vel [B,nv]) like mujoco_env.py:137-140."""

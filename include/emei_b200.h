@@ -168,6 +168,36 @@ int emei_i2p_step_f32(const float* state_in, float* state_out, float* obs_out, c
 int emei_i2p_step_f64(const double* state_in, double* state_out, double* obs_out, const void* action, double* reward,
                       uint8_t* done, double* stats, int64_t n, const emei_i2p_params* p, emei_stream_t stream);
 
+/* ---- per-sub-step Gaussian state noise ("obs_noise_params") -------------------
+ * Replaces mujoco_env.py:98-104: after EVERY sub-step the reference overwrites the simulator state with
+ * additive_gaussian_noise(qpos, qvel, obs_noise_params) (mujoco_env.py:197-249: one N(0, sigma_pos) /
+ * N(0, sigma_vel) draw per hinge/slide joint coordinate).  INTENDED semantics, like the init sampler: the
+ * reference slices rows instead of columns (:243-244), so with its batch of one it adds joint 0's draw to every
+ * coordinate and drops the other joints' (documented in DESIGN.md, not replicated).  The reference's stream is
+ * numpy's global Mersenne Twister; here coordinates 2k, 2k+1 of env e at global sub-step g = step * freq_rate + s
+ * are the Box-Muller pair of Philox4x32-10 block 4g + k keyed by (seed, env_offset + e): the result depends on
+ * neither the batch sharding nor the launch shape. */
+typedef struct emei_noise_params {
+  double sigma[6];     /* per state coordinate: IP [x, th, v, w] (first 4), I2P [x, th0, th1, v, w0, w1]; >= 0 */
+  uint64_t seed;       /* Philox key */
+  uint64_t env_offset; /* global id of env 0 (sharding) */
+  uint64_t step;       /* env-step counter of this call (the caller increments it every step) */
+} emei_noise_params;
+
+/* emei_cartpole_step_* for the EMEI_IP_* variants / emei_i2p_step_* with the noise above; same arguments. */
+int emei_ip_step_noisy_f32(const float* state_in, float* state_out, float* obs_out, const void* action, float* reward,
+                           uint8_t* done, double* stats, int64_t n, const emei_cartpole_params* p,
+                           const emei_noise_params* z, emei_stream_t stream);
+int emei_ip_step_noisy_f64(const double* state_in, double* state_out, double* obs_out, const void* action,
+                           double* reward, uint8_t* done, double* stats, int64_t n, const emei_cartpole_params* p,
+                           const emei_noise_params* z, emei_stream_t stream);
+int emei_i2p_step_noisy_f32(const float* state_in, float* state_out, float* obs_out, const void* action, float* reward,
+                            uint8_t* done, double* stats, int64_t n, const emei_i2p_params* p,
+                            const emei_noise_params* z, emei_stream_t stream);
+int emei_i2p_step_noisy_f64(const double* state_in, double* state_out, double* obs_out, const void* action,
+                            double* reward, uint8_t* done, double* stats, int64_t n, const emei_i2p_params* p,
+                            const emei_noise_params* z, emei_stream_t stream);
+
 /* ---- charged ball ----------------------------------------------------------------------------- */
 typedef struct emei_charged_ball_params {
   double gravity_acc, mass_ball, radius, charge, time_step; /* charged_ball.py:13-17 */

@@ -200,20 +200,22 @@ def ip_wrap_angle(theta):
     return (theta + np.pi) % (2 * np.pi) - np.pi
 
 
-def ip_step(state, ctrl, h, freq_rate, swingup: bool, p: InvertedPendulumParams, dtype=np.float64, libm=False):
+def ip_step(state, ctrl, h, freq_rate, swingup: bool, p: InvertedPendulumParams, dtype=np.float64, libm=False, noise=None):
     """Analytic IP step.  state [B,4] = [x, theta, v, omega] (qpos||qvel, mujoco_env.py:142-144),
     theta UNWRAPPED (the reference wraps only the observation copy, inverted_pendulum.py:45-49).
     Per sub-step (mujoco_env.py:91-97 with integrator="euler"): (q, v) <- (q + v*h, v + a(q,v)*h).
     Acceleration: cartpole.py:51-58 with theta_cartpole = theta (+ pi for SwingUp models, whose
     pole body is flipped by body_quat[2]=[0,0,1,0], inverted_pendulum.py:170-172).  Force =
-    gear*ctrl (inverted_pendulum.xml:23).  Returns (new_state, obs) with obs[:,1] wrapped."""
+    gear*ctrl (inverted_pendulum.xml:23).  Returns (new_state, obs) with obs[:,1] wrapped.
+    noise: optional [freq_rate, B, 4] float64 -- the already-scaled Gaussian draws that mujoco_env.py:98-104 adds to
+    (qpos, qvel) after every sub-step when obs_noise_params != 0 (added in float64, then cast to ``dtype``)."""
     T = np.dtype(dtype).type
     y = np.array(state, dtype=dtype, copy=True)
     force = T(p.gear) * np.asarray(ctrl, dtype=dtype).reshape(-1)
     h = T(h)
     sign = T(-1.0) if swingup else T(1.0)
     with np.errstate(all="ignore"):
-        for _ in range(int(freq_rate)):
+        for _ in range(int(freq_rate)):  # `_` indexes the noise of this sub-step
             x, theta, v, omega = y[:, 0], y[:, 1], y[:, 2], y[:, 3]
             if dtype == np.float64:
                 s, c = _sincos64(theta, libm)
@@ -222,6 +224,8 @@ def ip_step(state, ctrl, h, freq_rate, swingup: bool, p: InvertedPendulumParams,
             s, c = sign * s, sign * c
             x_acc, theta_acc = cartpole_accel(v, theta, omega, force, p, s, c)
             y = np.stack([x + v * h, theta + omega * h, v + x_acc * h, omega + theta_acc * h], axis=1)
+            if noise is not None:
+                y = (y.astype(np.float64) + np.asarray(noise[_], dtype=np.float64)).astype(dtype)
     obs = y.copy()
     obs[:, 1] = ip_wrap_angle(obs[:, 1]).astype(dtype)
     return y, obs
@@ -384,7 +388,7 @@ def i2p_wrap_obs(state):
     return obs
 
 
-def i2p_step(state, ctrl, h, freq_rate, swingup: bool, p: I2PParams, dtype=np.float64, libm=False):
+def i2p_step(state, ctrl, h, freq_rate, swingup: bool, p: I2PParams, dtype=np.float64, libm=False, noise=None):
     """Analytic I2P step.  state [B,6] = [x, th0, th1, v, w0, w1] (qpos||qvel, mujoco_env.py:142-144), angles
     unwrapped.  Per sub-step (mujoco_env.py:91-97, integrator="euler"): (q, v) <- (q + v h, v + a(q, v) h); force =
     gear * clip(ctrl) (inverted_double_pendulum.xml:45; mj_step clamps ctrl to ctrlrange).  -> (new_state, obs)."""
@@ -399,6 +403,8 @@ def i2p_step(state, ctrl, h, freq_rate, swingup: bool, p: I2PParams, dtype=np.fl
             q_new = y[:, :3] + y[:, 3:] * h
             v_new = y[:, 3:] + acc * h
             y[:, :3], y[:, 3:] = q_new, v_new
+            if noise is not None:  # mujoco_env.py:98-104: [freq_rate, B, 6] scaled Gaussian draws, added in float64
+                y = (y.astype(np.float64) + np.asarray(noise[_], dtype=np.float64)).astype(dtype)
         obs = i2p_wrap_obs(y)
     return y, obs
 

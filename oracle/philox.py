@@ -12,6 +12,7 @@ M0, M1 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57)
 W0, W1 = 0x9E3779B9, 0xBB67AE85
 MASK = np.uint64(0xFFFFFFFF)
 PURPOSE_UNIFORM, PURPOSE_GAUSSIAN, PURPOSE_CHARGED_BALL = 1, 2, 3
+PURPOSE_OBS_NOISE = 6
 
 
 def philox4x32_10(seed: int, env: np.ndarray, block: np.ndarray, purpose: int):
@@ -78,3 +79,23 @@ def init_charged_ball(n, radius, seed, env_offset=0, dtype=np.float64):
     x, y = np.sin(th) * T(radius), np.cos(th) * T(radius)
     free = np.stack([x, y, om * y, -om * x], axis=1).astype(dtype)
     return np.ones(n, dtype=np.uint8), np.stack([th, om], axis=1), free
+
+
+def obs_noise(n, dim, sigma, seed, step, freq_rate, env_offset=0):
+    """[freq_rate, n, dim] float64: the scaled Gaussian state noise of emei_*_step_noisy (kernels.cuh
+    add_state_noise; mujoco_env.py:98-104,197-249): coordinates 2k, 2k+1 of env e at global sub-step
+    g = step * freq_rate + s are sigma * (Box-Muller pair of Philox block 4 g + k)."""
+    env = np.arange(n, dtype=np.uint64) + np.uint64(env_offset)
+    sigma = np.asarray(sigma, dtype=np.float64)
+    out = np.empty((freq_rate, n, dim), dtype=np.float64)
+    for s in range(freq_rate):
+        g = step * freq_rate + s
+        for pr in range(dim // 2):
+            blk = 4 * g + pr
+            w = philox4x32_10(seed, env, np.full(n, blk & 0xFFFFFFFF), PURPOSE_OBS_NOISE | ((blk >> 32) << 8))
+            u1 = 1.0 - u01(w[0], w[1])
+            u2 = u01(w[2], w[3])
+            rad = np.sqrt(-2.0 * np.log(u1))
+            out[s, :, 2 * pr] = sigma[2 * pr] * (rad * np.cos(2 * np.pi * u2))
+            out[s, :, 2 * pr + 1] = sigma[2 * pr + 1] * (rad * np.sin(2 * np.pi * u2))
+    return out

@@ -26,17 +26,26 @@ def rollout_seeds(seed: int):
     return (seed * 0x9E3779B97F4A7C15 + 0x5851F42D4C957F2D) & MASK64, (seed * 0xD1B54A32D192ED03 + 0x14057B7EF767814F) & MASK64
 
 
+PURPOSE_ROLLOUT_RESET = 5
+
+
 def reset_sample_uniform(env_ids, ep_index, seed_reset, low=-0.05, high=0.05, pi_column=-1):
-    """float32 reset state of env ``env_ids[j]`` for its ``ep_index[j]``-th in-rollout episode."""
+    """float32 reset state of env ``env_ids[j]`` for its ``ep_index[j]``-th in-rollout episode: the lean sampler of
+    rollout_f32.cuh -- one Philox block per reset, coordinate c = float32 fma(high - low, u_c, low) with u_c the top
+    24 bits of word c (U(low, high) of cartpole.py:131-132,153-156), + pi on the swing-up angle added in float64."""
     env_ids = np.asarray(env_ids, dtype=np.uint64)
-    out = np.empty((env_ids.shape[0], 4), dtype=np.float32)
-    for j in range(env_ids.shape[0]):
+    m = env_ids.shape[0]
+    out = np.empty((m, 4), dtype=np.float32)
+    lo = np.float32(low)
+    span = np.float32(np.float32(high) - lo)
+    for j in range(m):
         s = (seed_reset + int(ep_index[j]) * RESET_STRIDE) & MASK64
-        for c in range(4):
-            v = low + (high - low) * P.uniform_column(s, env_ids[j : j + 1], c, P.PURPOSE_UNIFORM)[0]
-            if c == pi_column:
-                v = v + np.pi
-            out[j, c] = np.float32(v)
+        w = P.philox4x32_10(s, env_ids[j : j + 1], np.zeros(1), PURPOSE_ROLLOUT_RESET)[:, 0]
+        u = (w >> np.uint32(8)).astype(np.float32) * np.float32(1.0 / 16777216.0)  # exact: 24-bit integer * 2^-24
+        v = (np.float64(span) * u.astype(np.float64) + np.float64(lo)).astype(np.float32)  # one rounding = fmaf
+        if pi_column >= 0:
+            v[pi_column] = np.float32(np.float64(v[pi_column]) + np.pi)
+        out[j] = v
     return out
 
 

@@ -248,3 +248,25 @@ def test_shard_range_partitions_exactly():
             assert max(sizes) - min(sizes) <= 1
     with pytest.raises(ValueError):
         shard_range(10, 3, 2)
+
+
+def test_rollout_reset_sampler_mirror_is_uniform():
+    """The lean in-rollout reset sampler (oracle mirror of rollout_f32.cuh: one Philox block, 24-bit uniforms) draws
+    U(-0.05, 0.05) per coordinate (cartpole.py:131-132), + pi on the swing-up angle (cartpole.py:153-156); streams of
+    different envs / episodes are distinct."""
+    from scipy import stats
+
+    from oracle import rollout_oracle as RO
+
+    m = 4000
+    ids = np.arange(m)
+    s = RO.reset_sample_uniform(ids, np.ones(m, np.int64), 1234, pi_column=2)
+    assert s.dtype == np.float32 and s.shape == (m, 4)
+    s64 = s.astype(np.float64)
+    s64[:, 2] -= np.pi
+    assert np.all(s64 >= -0.05 - 1e-7) and np.all(s64 < 0.05 + 1e-7)
+    for c in range(4):
+        assert stats.kstest((s64[:, c] + 0.05) / 0.1, "uniform").pvalue > 1e-3
+    assert abs(np.corrcoef(s64[:, 0], s64[:, 1])[0, 1]) < 0.06
+    s2 = RO.reset_sample_uniform(ids, np.full(m, 2, np.int64), 1234, pi_column=2)
+    assert not np.array_equal(s, s2) and len(np.unique(s[:, 0])) > m * 0.99
