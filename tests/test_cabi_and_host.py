@@ -38,6 +38,34 @@ def test_struct_layouts_match_header():
     assert ctypes.sizeof(_lib.ChargedBallParams) == 5 * 8 + 2 * 4
     assert ctypes.sizeof(_lib.ScoringParams) == 2 * 4 + 13 * 8
     assert ctypes.sizeof(_lib.I2PParams) == 12 * 8 + 3 * 4 + 4  # padded to a multiple of 8
+    assert ctypes.sizeof(_lib.NoiseParams) == 6 * 8 + 3 * 8
+
+
+def test_noisy_step_validation_codes():
+    """emei_ip_step_noisy_* / emei_i2p_step_noisy_*: IP variants only, a noise struct is required, sigmas >= 0."""
+    lib = _lib.lib
+    p = _lib.CartPoleParams()
+    p.freq_rate, p.dt, p.variant, p.action_kind = 1, 0.02, _lib.IP_BOUNDARY_SWINGUP, 3
+    z = _lib.NoiseParams()
+    for f in (lib.emei_ip_step_noisy_f32, lib.emei_ip_step_noisy_f64):
+        assert f(None, None, None, None, None, None, None, 8, ctypes.byref(p), None, None) == -1
+        assert f(None, None, None, None, None, None, None, 0, ctypes.byref(p), ctypes.byref(z), None) == 0
+        assert f(None, None, None, None, None, None, None, 8, ctypes.byref(p), ctypes.byref(z), None) == -1  # null state
+        p.variant = _lib.CARTPOLE_SWINGUP  # the classic-control family has no obs_noise_params (base_control.py:14-16)
+        assert f(None, None, None, None, None, None, None, 8, ctypes.byref(p), ctypes.byref(z), None) == -2
+        p.variant = _lib.IP_BOUNDARY_SWINGUP
+        z.sigma[2] = -1.0
+        assert f(None, None, None, None, None, None, None, 8, ctypes.byref(p), ctypes.byref(z), None) == -6
+        z.sigma[2] = 0.0
+    q = _lib.I2PParams()
+    q.freq_rate, q.dt, q.variant, q.action_kind = 1, 0.02, _lib.I2P_BOUNDARY_SWINGUP, 3
+    q.mass_cart = q.mass_pole0 = q.mass_pole1 = q.length0 = q.length1 = 1.0
+    for f in (lib.emei_i2p_step_noisy_f32, lib.emei_i2p_step_noisy_f64):
+        assert f(None, None, None, None, None, None, None, 8, ctypes.byref(q), None, None) == -1
+        z.sigma[5] = float("nan")
+        assert f(None, None, None, None, None, None, None, 8, ctypes.byref(q), ctypes.byref(z), None) == -6
+        z.sigma[5] = 0.0
+        assert f(None, None, None, None, None, None, None, 0, ctypes.byref(q), ctypes.byref(z), None) == 0
 
 
 def test_argument_validation_codes():
@@ -270,3 +298,21 @@ def test_rollout_reset_sampler_mirror_is_uniform():
     assert abs(np.corrcoef(s64[:, 0], s64[:, 1])[0, 1]) < 0.06
     s2 = RO.reset_sample_uniform(ids, np.full(m, 2, np.int64), 1234, pi_column=2)
     assert not np.array_equal(s, s2) and len(np.unique(s[:, 0])) > m * 0.99
+
+
+def test_obs_noise_mirror_is_gaussian_and_step_keyed():
+    """oracle/philox.py obs_noise (mirror of kernels.cuh add_state_noise): N(0, sigma) per coordinate, a fresh draw
+    per (env, env step, sub-step), independent of how the batch is sharded."""
+    from scipy import stats
+
+    from oracle import philox as P
+
+    n, sig = 20000, np.array([0.01, 0.02, 0.0, 0.5])
+    z = P.obs_noise(n, 4, sig, 99, 3, 2)
+    assert z.shape == (2, n, 4) and np.all(z[:, :, 2] == 0.0)
+    for c in (0, 1, 3):
+        assert abs(z[0, :, c].std() / sig[c] - 1) < 0.03
+        assert stats.kstest(z[1, :, c] / sig[c], "norm").pvalue > 1e-3
+    assert abs(np.corrcoef(z[0, :, 0], z[0, :, 1])[0, 1]) < 0.03 and abs(np.corrcoef(z[0, :, 0], z[1, :, 0])[0, 1]) < 0.03
+    assert not np.array_equal(z, P.obs_noise(n, 4, sig, 99, 4, 2))
+    assert np.array_equal(z[:, 5000:], P.obs_noise(n - 5000, 4, sig, 99, 3, 2, env_offset=5000))

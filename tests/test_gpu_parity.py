@@ -1081,5 +1081,94 @@ def test_i2p_reset_freeze_next_obs_and_graph():
     assert torch.equal(env.state, snap) and env.frozen is False
     g = env.get_transition_graph()
     assert g.shape == (7, 6) and g[6].tolist() == [0, 0, 0, 1, 1, 1]
+
+
+# ================================================================================================
+# obs_noise_params: Gaussian state noise after every sub-step (mujoco_env.py:98-104)
+# ================================================================================================
+NOISE_MUL, NOISE_ADD = 0xA24BAED4963EE407, 0x9FB21C651E98DF25  # EmeiMujocoEnv._next_obs_noise
+
+
+def _noise_seed(seed):
+    return (seed * NOISE_MUL + NOISE_ADD) & 0xFFFFFFFFFFFFFFFF
+
+
+@pytest.mark.parametrize("dtype", (torch.float64, torch.float32))
+@pytest.mark.parametrize("fr", (1, 4))
+def test_ip_obs_noise_vs_oracle_and_philox_mirror(dtype, fr):
+    """Two consecutive noisy steps against the oracle fed with the Philox mirror's draws (teacher-forced), in both
+    precisions; the (sigma_pos, sigma_vel) tuple form; sharded == unsharded."""
+    n, kind = 2048, "ip_boundary_swingup"
+    st, act = ip_inputs(4001, n)
+    st[: n // 8, 1] /= 30.0
+    if dtype == torch.float32:
+        st = st.astype(np.float32).astype(np.float64)
+    p = O.InvertedPendulumParams()
+    ctrl = np.clip(act.astype(np.float64), p.ctrl_low, p.ctrl_high)
+    sig = np.array([0.01, 0.01, 0.03, 0.03])
+    env = E.make(IP[kind], freq_rate=fr, num_envs=n, dtype=dtype, obs_noise_params=(0.01, 0.03))
+    env.reset(seed=11)
+    cur = st
+    for step in range(2):
+        env.state = cur
+        obs, rew, done, _, _ = env.step(act)
+        z = P.obs_noise(n, 4, sig, _noise_seed(11), step, fr)
+        ref_state, ref_obs = O.ip_step(cur, ctrl, 0.02, fr, True, p, libm=True, noise=z)
+        got = env.state.cpu().numpy().astype(np.float64)
+        if dtype == torch.float64:
+            assert close64(got, ref_state, 1e-11)
+        else:
+            assert within32(got, ref_state, 1.5).all()
+        clean, _ = O.ip_step(cur, ctrl, 0.02, fr, True, p, libm=True)
+        d = got - clean
+        assert 0.5 * sig[0] < d[:, 0].std() and d[:, 2].std() > 0.5 * sig[2]  # the noise is really there
+        assert within32(rew.cpu().numpy(), O.ip_reward(kind, ref_obs), 3.0).all()
+        cur = got
+    # sharding: the second half of the batch as its own env with env_offset = n/2 draws the same noise
+    half = E.make(IP[kind], freq_rate=fr, num_envs=n // 2, dtype=dtype, obs_noise_params=(0.01, 0.03), env_offset=n // 2)
+    full = E.make(IP[kind], freq_rate=fr, num_envs=n, dtype=dtype, obs_noise_params=(0.01, 0.03))
+    half.reset(seed=11)
+    full.reset(seed=11)
+    half.state, full.state = st[n // 2 :], st
+    half.step(act[n // 2 :])
+    full.step(act)
+    assert torch.equal(half.state, full.state[n // 2 :])
     with pytest.raises(NotImplementedError):
-        E.make("BoundaryInvertedDoublePendulumSwingUp-v0", obs_noise_params=0.1)
+        full.rollout(4)
+
+
+def test_obs_noise_forms_moments_and_i2p():
+    """scalar / dict forms (mujoco_env.py:217-227), the moments of the added noise, the I2P family, and zero noise
+    == the plain step bit for bit."""
+    from scipy import stats
+
+    n = 1 << 15
+    st, act = ip_inputs(4002, n)
+    env = E.make(IP["ip_rebound_swingup"], num_envs=n, dtype=torch.float64, obs_noise_params={1: (0.0, 0.05)})
+    clean = E.make(IP["ip_rebound_swingup"], num_envs=n, dtype=torch.float64)
+    env.reset(seed=3)
+    clean.reset(seed=3)
+    env.state, clean.state = st, st
+    env.step(act)
+    clean.step(act)
+    d = (env.state - clean.state).cpu().numpy()
+    assert np.all(d[:, [0, 1, 2]] == 0.0)  # only joint 1's velocity is noisy
+    assert abs(d[:, 3].std() - 0.05) < 0.002 and abs(d[:, 3].mean()) < 0.002
+    assert stats.kstest(d[:, 3] / 0.05, "norm").pvalue > 1e-3
+    # I2P, float64, scalar form, two sub-steps
+    m = 4096
+    st6, act6 = i2p_inputs(4003, m)
+    p6 = O.I2PParams()
+    e6 = E.make(I2P["i2p_boundary_swingup"], freq_rate=2, num_envs=m, dtype=torch.float64, obs_noise_params=0.02)
+    e6.reset(seed=5)
+    e6.state = st6
+    obs6, rew6, done6, _, _ = e6.step(act6)
+    z6 = P.obs_noise(m, 6, np.full(6, 0.02), _noise_seed(5), 0, 2)
+    ref6, _ = O.i2p_step(st6, act6.astype(np.float64), 0.02, 2, True, p6, libm=True, noise=z6)
+    assert close64(e6.state.cpu().numpy(), ref6, 1e-10)
+    assert np.allclose(obs6.cpu().numpy(), O.i2p_wrap_obs(e6.state.cpu().numpy()), rtol=0, atol=1e-12)
+    # zero noise takes the plain kernels
+    e0 = E.make(I2P["i2p_boundary_swingup"], freq_rate=2, num_envs=m, dtype=torch.float64, obs_noise_params=0.0)
+    e1 = E.make(I2P["i2p_boundary_swingup"], freq_rate=2, num_envs=m, dtype=torch.float64)
+    e0.state, e1.state = st6, st6
+    assert torch.equal(e0.step(act6)[0], e1.step(act6)[0])
