@@ -206,11 +206,11 @@ class CartPoleStep(Workload):
 
     key, metric, unit = "c2", "env_steps_per_sec", "env-steps/s"
     name = "ContinuousCartPoleSwingUp batched step, 2^20 envs/GPU, freq_rate=4, float32 (BASELINE configs[1])"
-    kernel = "emei::cartpole_step_f32_kernel<IP=0, AK=f32, FR=4>"
+    kernel = "emei::cartpole_step_f32_tma_kernel<IP=0, AK=f32, FR=4, HAS_OBS=0>"
     env_id, n_envs, freq_rate, ring = "ContinuousCartPoleSwingUp-v0", 1 << 20, 4, 8
     alg_bytes = 41  # state 16 + action 4 + next 16 + reward 4 + done 1
     cpu_kind = "c2"
-    inst_per_unit = 209.0  # warp-level SASS instructions per env-step (packed f32x2: one FFMA2 serves two envs), ncu smsp__inst_executed (profiles/)
+    inst_per_unit = 179.1  # thread-level SASS instructions per env-step = 32 x smsp__inst_executed / envs (packed f32x2: one FFMA2 serves two envs); ncu, profiles/r01_launches_bench_c2.csv
 
     def synth(self, seed):
         return synth_cartpole(self.n_envs, seed)
@@ -264,14 +264,23 @@ class CartPoleStep(Workload):
 class IPStep(CartPoleStep):
     key = "c1"
     name = "BoundaryInvertedPendulumSwingUp batched step, 4096 envs, freq_rate=1, float32 (BASELINE configs[0])"
-    kernel = "emei::cartpole_step_f32_kernel<IP=1, AK=f32, FR=1>"
+    kernel = "emei::cartpole_step_f32_small_kernel<IP=1, AK=f32, FR=1, HAS_OBS=1>"
     env_id, n_envs, freq_rate, ring = "BoundaryInvertedPendulumSwingUp-v0", 4096, 1, 1024
     alg_bytes = 57  # state 16 + action 4 + next state 16 + wrapped obs 16 + reward 4 + done 1
     cpu_kind, cpu_sample = "c1", 1 << 20
-    inst_per_unit = 130.0
+    inst_per_unit = 202.5  # one env per thread, 128-thread CTAs: profiles/r01_launches_bench_c1.csv
 
     def synth(self, seed):
         return synth_ip(self.n_envs, seed)
+
+
+class CartPoleStepLarge(CartPoleStep):
+    """The C2 step at 2^24 envs per GPU: launch ramp and drain amortised, the kernel's steady state (recycled TMA ring)."""
+
+    key = "c2_large"
+    name = "ContinuousCartPoleSwingUp batched step, 2^24 envs/GPU, freq_rate=4, float32 (C2's kernel at 16x the batch)"
+    n_envs, ring = 1 << 24, 2
+    use_graph = False
 
 
 class Scoring(Workload):
@@ -442,7 +451,7 @@ class CartPoleRollout(Workload):
     use_graph, bound = False, "issue"
     record = False
     alg_bytes = 0.0  # set in setup(): per env-step
-    inst_per_unit = 349.0  # warp-level SASS instructions per env-step incl. divergent in-kernel resets (ncu smsp__inst_executed, profiles/r01_launches_rollout*.csv)
+    inst_per_unit = 247.1  # thread-level SASS instructions per env-step incl. divergent in-kernel resets (32 x smsp__inst_executed / env-steps; ncu, profiles/r01_launches_rollout*.csv)
     cpu_kind = "c2"
     e2e_max_steps = 5
 
@@ -491,7 +500,7 @@ class CartPoleRolloutRecord(CartPoleRollout):
     name = CartPoleRollout.name.replace("fused rollout", "fused rollout + transition records (dataset layout)")
     kernel = "emei::cartpole_rollout_f32_kernel<IP=0, AK=f32, FR=4, RECORD=1>"
     record = True
-    inst_per_unit = 382.0  # t_issue = 0.34 ms > t_hbm = 0.22 ms (42 B/env-step) at 2^25 env-steps per launch: still issue-bound
+    inst_per_unit = 289.9  # (ncu, profiles/r01_launches_rollout_rec.csv) t_issue = 0.26 ms > t_hbm = 0.22 ms (42 B/env-step) at 2^25 env-steps per launch: still issue-bound
 
     def setup(self):
         if not self.args.horizon_set:
@@ -558,7 +567,7 @@ class ChargedBallRollout(Workload):
                 "l2_policy": f"no reuse to defeat: {self.n * 37 / 1e6:.0f} MB of state read once and written once per launch"}
 
 
-WORKLOADS = {w.key: w for w in (IPStep, CartPoleStep, HopperScoring, HalfCheetahScoring, ChargedBall, ScoringSweep,
+WORKLOADS = {w.key: w for w in (IPStep, CartPoleStep, CartPoleStepLarge, HopperScoring, HalfCheetahScoring, ChargedBall, ScoringSweep,
                                 CartPoleRollout, CartPoleRolloutRecord, ChargedBallRollout)}
 
 

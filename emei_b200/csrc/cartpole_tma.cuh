@@ -1,16 +1,17 @@
-// float32 cart-pole / analytic inverted-pendulum step, TMA-staged: the shape used for every batch that is
-// 16-byte aligned (the per-thread cp.async kernel of cartpole_f32.cuh remains for misaligned action arrays).
+// float32 cart-pole / analytic inverted-pendulum step, TMA-staged.
 //
 // At BASELINE configs[1] (2^20 envs, 41 B/env-step) one SM's share of a step is 7 085 envs = 142 KB of inputs:
-// it FITS in the SM's 227 KB of shared memory.  So the kernel is one persistent CTA per SM whose producer warp
-// issues, at t = 0, one 1-D bulk copy (cp.async.bulk, the TMA engine) per 512-env chunk for as many chunks as the
-// ring holds -- every input byte of the step is in flight within the first microsecond, HBM streams at full
-// rate from the start, and no thread spends instructions or LDGSTS slots on address generation -- while three
-// consumer groups of 256 threads each take chunks as their mbarriers complete, advance TWO envs per thread
-// with the packed f32x2 arithmetic of f32math.cuh and store the results.  Larger batches recycle the ring
-// (empty mbarriers).  For a step kernel this short (~9 us) the ramp matters as much as the steady state:
+// it FITS in the SM's 227 KB of shared memory.  So the kernel is one persistent CTA per SM (1024 threads = four
+// consumer groups of 256) that requests, at t = 0, one 1-D bulk copy (cp.async.bulk, the TMA engine) per 512-env
+// chunk for as many chunks as the ring holds -- every input byte of the step is in flight within the first
+// microsecond, HBM streams at full rate from the start, and no thread spends instructions or LDGSTS slots on
+// address generation -- while the groups take their chunks as the mbarriers complete, advance TWO envs per thread
+// with the packed f32x2 arithmetic of f32math.cuh and store the results.  Larger batches recycle the ring: every
+// group owns a quarter of the slots and refills its own (empty mbarriers), which streams 2^26 envs at 0.97 of the
+// measured HBM peak.  For a step this short (~10 us at 2^20) the ramp matters as much as the steady state:
 // per-thread prefetch rings issue a slot's refill only after that slot's math, which left HBM idle during
-// the compute of the first chunks (ncu: dram 18 %, issue 55 %, profiles/r01_ncu_kb_packed.txt).
+// the compute of the first chunks (ncu: dram 18 %, issue 55 %, profiles/r01_kbench_cartpole_variants.txt).
+// Batches below kSmallBatch take a plain one-env-per-thread kernel (launch latency is their whole cost).
 //
 // Chunk c = envs [512 c, 512 c + 512): thread t of a group owns envs 512 c + t and 512 c + 256 + t.
 #pragma once

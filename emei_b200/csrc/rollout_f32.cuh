@@ -5,7 +5,8 @@
 // for a batch of independent envs, with gym's TimeLimit (register_env.py max_episode_steps: truncated when
 // the episode step count reaches the limit) and auto-reset (zoo/util.py:52-54) done in-kernel.
 //
-// One thread owns one env for the whole horizon: the env's state, the episode step counter and the
+// One thread owns its envs (two for the cart-pole family, whose pair shares packed f32x2 arithmetic; one for
+// the charged ball) for the whole horizon: state, episode step counter and
 // episode return live in registers across all T steps, so HBM is touched only for what the caller asks
 // for -- the action stream (teacher-forced policy) and/or the transition records in the reference's
 // dataset layout (observations, next_observations, actions, rewards, dones, timeouts; zoo/util.py:62-67).
@@ -111,7 +112,11 @@ struct CartPoleDyn {
   using Consts = CartPoleF32Consts;
   using ActT = typename ActionStorage<AK>::type;
   static constexpr bool kDiscrete = AK <= EMEI_ACTION_DISCRETE_I64;
-  static constexpr int kMinBlocks = 4;
+  // TWO envs per thread: the dynamics of the pair run in packed f32x2 registers (the step kernel's arithmetic,
+  // f32::cartpole_integrate<f2>), which halves the issue slots of the integration; policy, TimeLimit bookkeeping and
+  // resets stay per env.
+  static constexpr int kEnvsPerThread = 2;
+  static constexpr int kMinBlocks = 3;  // 80 registers, no spills; 4 CTAs/SM (64 registers, 128 B of spills) measured the same 101 G env-steps/s
   struct Buffers {
     float4* state;
   };
@@ -119,19 +124,58 @@ struct CartPoleDyn {
     float4 y;
   };
   __device__ __forceinline__ static void load(Regs& e, const Buffers& b, uint32_t i) { e.y = b.state[i]; }
+  __device__ __forceinline__ static void blank(Regs& e) { e.y = make_float4(0.f, 0.f, 0.f, 0.f); }
   __device__ __forceinline__ static void store(const Regs& e, const Buffers& b, uint32_t i) { b.state[i] = e.y; }
   __device__ __forceinline__ static float4 observation(const Regs& e) {
     return IP ? make_float4(e.y.x, wrap_pi_f32(e.y.y), e.y.z, e.y.w) : e.y;
   }
-  // the scalar (one env per thread) form of the arithmetic of cartpole_step_f32_tma_kernel: same bits
-  __device__ __forceinline__ static void step(Regs& e, float a, const Consts& k, float& rew, bool& terminated, float4& next_obs) {
+  // one step of the pair: same bits as two lanes of cartpole_step_f32_tma_kernel / as cartpole_step_one per env
+  __device__ __forceinline__ static void step(Regs (&e)[2], const float (&a)[2], const Consts& k, float (&rew)[2],
+                                              bool (&terminated)[2], float4 (&next_obs)[2]) {
+    using f32::f2;
     const uint32_t flip = ip_flip(IP, k.variant);
-    const float f_mt = action_to_f_mt<IP, AK>(a, k);
-    float4 y = e.y;
-    bool notdone;
-    cartpole_step_one<IP, FR>(y, f_mt, flip, k, rew, notdone, next_obs);
-    e.y = y;
-    terminated = !notdone;
+    const float fa = action_to_f_mt<IP, AK>(a[0], k), fb = action_to_f_mt<IP, AK>(a[1], k);
+    const float4 ya = e[0].y, yb = e[1].y;
+    f2 X = f32::f2_pack(ya.x, yb.x), V, TH, W = f32::f2_pack(ya.w, yb.w);
+    if constexpr (!IP) {
+      V = f32::f2_pack(ya.y, yb.y);
+      TH = f32::f2_pack(ya.z, yb.z);
+    } else {
+      TH = f32::f2_pack(ya.y, yb.y);
+      V = f32::f2_pack(ya.z, yb.z);
+    }
+    const float th0a = fabsf(IP ? ya.y : ya.z), th0b = fabsf(IP ? yb.y : yb.z);
+    f32::LaneMax<f2> dmax;
+    const f2 C = f32::cartpole_integrate<f2, FR>(X, V, TH, W, f32::f2_pack(-fa, -fb), flip, k.k, k.freq_rate, dmax);
+    float4 na, nb;
+    {
+      float t0, t1;
+      f32::f2_unpack(X, na.x, nb.x);
+      f32::f2_unpack(W, na.w, nb.w);
+      f32::f2_unpack(V, t0, t1);
+      if constexpr (!IP) { na.y = t0; nb.y = t1; } else { na.z = t0; nb.z = t1; }
+      f32::f2_unpack(TH, t0, t1);
+      if constexpr (!IP) { na.z = t0; nb.z = t1; } else { na.y = t0; nb.y = t1; }
+    }
+    float ca, cb;
+    f32::f2_unpack(C, ca, cb);
+    if constexpr (IP) {
+      ca = f32::u2f(f32::f2u(ca) ^ flip);
+      cb = f32::u2f(f32::f2u(cb) ^ flip);
+    }
+    const bool ok_a = th0a <= f32::kSinCosSaneMax && dmax.a <= f32::kDeltaMax;
+    const bool ok_b = th0b <= f32::kSinCosSaneMax && dmax.b <= f32::kDeltaMax;
+    if (!(ok_a && ok_b)) {  // cold: the integrator's guard tripped (f32math.cuh)
+      if (!ok_a) na = integrate_libm<IP, FR>(ya, fa, flip, k.k, k.freq_rate);
+      if (!ok_b) nb = integrate_libm<IP, FR>(yb, fb, flip, k.k, k.freq_rate);
+    }
+    bool nd_a, nd_b;
+    cartpole_outcome<IP>(na, ok_a, ca, k, rew[0], nd_a, next_obs[0]);
+    cartpole_outcome<IP>(nb, ok_b, cb, k, rew[1], nd_b, next_obs[1]);
+    e[0].y = na;
+    e[1].y = nb;
+    terminated[0] = !nd_a;
+    terminated[1] = !nd_b;
   }
   __device__ __forceinline__ static void reset(Regs& e, const RolloutConsts& r, const Consts&, unsigned long long env, unsigned long long seed) {
     e.y = rollout_init_state(r, env, seed);
@@ -150,6 +194,8 @@ struct ChargedBallDyn {
     float4* free_state;
   };
   using Regs = CBRegs;
+  static constexpr int kEnvsPerThread = 1;
+  __device__ __forceinline__ static void blank(Regs&) {}
   __device__ __forceinline__ static void load(Regs& e, const Buffers& b, uint32_t i) {
     e.on = b.on_circle[i] != 0;
     const float2 c2 = b.circle[i];
@@ -164,10 +210,11 @@ struct ChargedBallDyn {
     b.free_state[i] = e.f;
   }
   __device__ __forceinline__ static float4 observation(const Regs& e) { return e.f; }  // charged_ball.py:96-97
-  __device__ __forceinline__ static void step(Regs& e, float a, const Consts& k, float& rew, bool& terminated, float4& next_obs) {
-    rew = cb_env_step(e, cb_field<AK>(a, k), k);
-    terminated = false;  // charged_ball.py:110-111
-    next_obs = e.f;
+  __device__ __forceinline__ static void step(Regs (&e)[1], const float (&a)[1], const Consts& k, float (&rew)[1],
+                                              bool (&terminated)[1], float4 (&next_obs)[1]) {
+    rew[0] = cb_env_step(e[0], cb_field<AK>(a[0], k), k);
+    terminated[0] = false;  // charged_ball.py:110-111
+    next_obs[0] = e[0].f;
   }
   __device__ __forceinline__ static void reset(Regs& e, const RolloutConsts&, const Consts& k, unsigned long long env, unsigned long long seed) {
     e = rollout_init_charged_ball(k.r, env, seed);
@@ -191,93 +238,125 @@ struct RolloutIO {  // everything that is not the env family's own state
   double* stats;
 };
 
+// One thread owns E = Dyn::kEnvsPerThread envs for the whole horizon: envs i0 + e * kBlock of its CTA's block of
+// E * kBlock envs (every access stays coalesced per e).
 template <class Dyn, bool RECORD>
 __global__ void __launch_bounds__(kBlock, Dyn::kMinBlocks)
     rollout_f32_kernel(const typename Dyn::Buffers b, const RolloutIO io, uint32_t n, const typename Dyn::Consts k,
                        const RolloutConsts r) {
   using ActT = typename Dyn::ActT;
-  const uint32_t i = blockIdx.x * kBlock + threadIdx.x;
-  const bool live = i < n;
+  constexpr int E = Dyn::kEnvsPerThread;
+  const uint32_t i0 = blockIdx.x * (kBlock * E) + threadIdx.x;
   const ActT* __restrict__ act_in = static_cast<const ActT*>(io.actions);
   ActT* __restrict__ act_out = static_cast<ActT*>(io.rec_act);
-  const unsigned long long env = r.env_offset + i;
 
-  float r_sum = 0.f, fin_ret = 0.f;
+  // reward sums in double: a thread's partial sums must not depend on how a horizon is split into launches
+  double r_sum = 0.0, fin_ret = 0.0;
   unsigned n_term = 0, n_trunc = 0, n_fin = 0, fin_len = 0;
   pdl_trigger();
   pdl_wait();
-  if (live) {
-    typename Dyn::Regs e;
-    Dyn::load(e, b, i);
-    int ep_step = io.ep_step[i];
-    float ep_ret = io.ep_return[i];
-    int ep_idx = io.ep_index[i];
-    uint32_t w[4] = {0, 0, 0, 0};
-    float a_next = 0.f;
-    if (!r.random_policy) a_next = static_cast<float>(__ldg(act_in + i));
-    for (int t = 0; t < r.horizon; ++t) {
-      // ---- policy
-      float a;
-      if (r.random_policy) {  // env.action_space.sample() (zoo/util.py:57): Discrete(2) bit / Box uniform
-        // counter-based stream per (seed_action, env): Discrete(2) consumes ONE bit per step (a 128-bit Philox
-        // block lasts 128 steps), Box one 32-bit word per step (top 24 bits -> [low, high))
-        const unsigned long long tg = r.t0 + static_cast<unsigned long long>(t);
-        if constexpr (Dyn::kDiscrete) {
-          if (t == 0 || (tg & 127ull) == 0) Philox::generate(r.seed_action, env, static_cast<uint32_t>(tg >> 7), kPurposeRolloutAction, w);
-          const uint32_t word = select_word(w, static_cast<unsigned>(tg >> 5) & 3u);
-          a = static_cast<float>((word >> (static_cast<unsigned>(tg) & 31u)) & 1u);
-        } else {
-          if (t == 0 || (tg & 3ull) == 0) Philox::generate(r.seed_action, env, static_cast<uint32_t>(tg >> 2), kPurposeRolloutAction, w);
-          const uint32_t word = select_word(w, static_cast<unsigned>(tg) & 3u);
-          a = fmaf(r.act_high - r.act_low, static_cast<float>(word >> 8) * (1.0f / 16777216.0f), r.act_low);
-        }
+  if (i0 < n) {
+    typename Dyn::Regs ev[E];
+    uint32_t idx[E];
+    bool live[E];
+    int ep_step[E], ep_idx[E];
+    float ep_ret[E], a_next[E];
+    uint32_t w[E][4];
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      idx[e] = i0 + static_cast<uint32_t>(e) * kBlock;
+      live[e] = idx[e] < n;
+      ep_step[e] = ep_idx[e] = 0;
+      ep_ret[e] = a_next[e] = 0.f;
+      w[e][0] = w[e][1] = w[e][2] = w[e][3] = 0u;
+      if (live[e]) {
+        Dyn::load(ev[e], b, idx[e]);
+        ep_step[e] = io.ep_step[idx[e]];
+        ep_ret[e] = io.ep_return[idx[e]];
+        ep_idx[e] = io.ep_index[idx[e]];
+        if (!r.random_policy) a_next[e] = static_cast<float>(__ldg(act_in + idx[e]));
       } else {
-        a = a_next;
-        if (t + 1 < r.horizon) a_next = static_cast<float>(__ldg(act_in + static_cast<size_t>(t + 1) * n + i));
-      }
-      const size_t rec = static_cast<size_t>(t) * n + i;
-      if constexpr (RECORD) {
-        io.rec_obs[rec] = Dyn::observation(e);
-        act_out[rec] = static_cast<ActT>(a);
-      }
-      // ---- dynamics + reward + terminal (the step kernel's arithmetic)
-      float rew;
-      bool terminated;
-      float4 next_obs;
-      Dyn::step(e, a, k, rew, terminated, next_obs);
-      // ---- TimeLimit + bookkeeping (zoo/util.py:58-73; gym TimeLimit: truncated = elapsed >= max)
-      ep_step += 1;
-      ep_ret += rew;
-      const bool truncated = r.max_episode_steps > 0 && ep_step >= r.max_episode_steps;
-      const bool done = terminated || truncated;
-      if constexpr (RECORD) {
-        io.rec_next[rec] = next_obs;
-        io.rec_rew[rec] = rew;
-        io.rec_done[rec] = done ? 1 : 0;
-        io.rec_timeout[rec] = truncated ? 1 : 0;
-      }
-      r_sum += rew;
-      n_term += terminated ? 1u : 0u;
-      n_trunc += truncated ? 1u : 0u;
-      if (done && r.auto_reset) {
-        n_fin += 1u;
-        fin_ret += ep_ret;
-        fin_len += static_cast<unsigned>(ep_step);
-        ep_idx += 1;
-        Dyn::reset(e, r, k, env, r.seed_reset + static_cast<unsigned long long>(ep_idx) * 0xD1B54A32D192ED03ull);
-        ep_step = 0;
-        ep_ret = 0.f;
+        Dyn::blank(ev[e]);  // a dead lane of the pair computes on zeros; nothing of it is stored or counted
       }
     }
-    Dyn::store(e, b, i);
-    io.ep_step[i] = ep_step;
-    io.ep_return[i] = ep_ret;
-    io.ep_index[i] = ep_idx;
+    for (int t = 0; t < r.horizon; ++t) {
+      float a[E];
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        // ---- policy
+        if (r.random_policy) {  // env.action_space.sample() (zoo/util.py:57): Discrete(2) bit / Box uniform
+          // counter-based stream per (seed_action, env): Discrete(2) consumes ONE bit per step (a 128-bit Philox
+          // block lasts 128 steps), Box one 32-bit word per step (top 24 bits -> [low, high))
+          const unsigned long long env = r.env_offset + idx[e];
+          const unsigned long long tg = r.t0 + static_cast<unsigned long long>(t);
+          if constexpr (Dyn::kDiscrete) {
+            if (t == 0 || (tg & 127ull) == 0) Philox::generate(r.seed_action, env, static_cast<uint32_t>(tg >> 7), kPurposeRolloutAction, w[e]);
+            const uint32_t word = select_word(w[e], static_cast<unsigned>(tg >> 5) & 3u);
+            a[e] = static_cast<float>((word >> (static_cast<unsigned>(tg) & 31u)) & 1u);
+          } else {
+            if (t == 0 || (tg & 3ull) == 0) Philox::generate(r.seed_action, env, static_cast<uint32_t>(tg >> 2), kPurposeRolloutAction, w[e]);
+            const uint32_t word = select_word(w[e], static_cast<unsigned>(tg) & 3u);
+            a[e] = fmaf(r.act_high - r.act_low, static_cast<float>(word >> 8) * (1.0f / 16777216.0f), r.act_low);
+          }
+        } else {
+          a[e] = a_next[e];
+          if (live[e] && t + 1 < r.horizon) a_next[e] = static_cast<float>(__ldg(act_in + static_cast<size_t>(t + 1) * n + idx[e]));
+        }
+        if constexpr (RECORD) {
+          if (live[e]) {
+            const size_t rec = static_cast<size_t>(t) * n + idx[e];
+            io.rec_obs[rec] = Dyn::observation(ev[e]);
+            act_out[rec] = static_cast<ActT>(a[e]);
+          }
+        }
+      }
+      // ---- dynamics + reward + terminal (the step kernel's arithmetic)
+      float rew[E];
+      bool terminated[E];
+      float4 next_obs[E];
+      Dyn::step(ev, a, k, rew, terminated, next_obs);
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        if (!live[e]) continue;
+        // ---- TimeLimit + bookkeeping (zoo/util.py:58-73; gym TimeLimit: truncated = elapsed >= max)
+        ep_step[e] += 1;
+        ep_ret[e] += rew[e];
+        const bool truncated = r.max_episode_steps > 0 && ep_step[e] >= r.max_episode_steps;
+        const bool done = terminated[e] || truncated;
+        if constexpr (RECORD) {
+          const size_t rec = static_cast<size_t>(t) * n + idx[e];
+          io.rec_next[rec] = next_obs[e];
+          io.rec_rew[rec] = rew[e];
+          io.rec_done[rec] = done ? 1 : 0;
+          io.rec_timeout[rec] = truncated ? 1 : 0;
+        }
+        r_sum += static_cast<double>(rew[e]);
+        n_term += terminated[e] ? 1u : 0u;
+        n_trunc += truncated ? 1u : 0u;
+        if (done && r.auto_reset) {
+          n_fin += 1u;
+          fin_ret += static_cast<double>(ep_ret[e]);
+          fin_len += static_cast<unsigned>(ep_step[e]);
+          ep_idx[e] += 1;
+          Dyn::reset(ev[e], r, k, r.env_offset + idx[e], r.seed_reset + static_cast<unsigned long long>(ep_idx[e]) * 0xD1B54A32D192ED03ull);
+          ep_step[e] = 0;
+          ep_ret[e] = 0.f;
+        }
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      if (!live[e]) continue;
+      Dyn::store(ev[e], b, idx[e]);
+      io.ep_step[idx[e]] = ep_step[e];
+      io.ep_return[idx[e]] = ep_ret[e];
+      io.ep_index[idx[e]] = ep_idx[e];
+    }
   }
   if (io.stats != nullptr) {  // uniform across the grid
     __shared__ double s_red[kBlock / 32];
-    const double vals[6] = {static_cast<double>(r_sum), static_cast<double>(n_term), static_cast<double>(n_trunc),
-                            static_cast<double>(n_fin), static_cast<double>(fin_ret), static_cast<double>(fin_len)};
+    const double vals[6] = {r_sum, static_cast<double>(n_term), static_cast<double>(n_trunc),
+                            static_cast<double>(n_fin), fin_ret, static_cast<double>(fin_len)};
 #pragma unroll
     for (int j = 0; j < 6; ++j) {
       const double tot = block_sum_double(vals[j], s_red);
@@ -289,7 +368,7 @@ __global__ void __launch_bounds__(kBlock, Dyn::kMinBlocks)
 template <class Dyn>
 inline void launch_rollout(const typename Dyn::Buffers& b, const RolloutIO& io, int64_t n, const typename Dyn::Consts& k,
                            const RolloutConsts& r, cudaStream_t s) {
-  const int grid = grid_for(n, kBlock);
+  const int grid = grid_for(n, kBlock * Dyn::kEnvsPerThread);
   if (io.rec_obs != nullptr)
     launch_pdl(rollout_f32_kernel<Dyn, true>, grid, kBlock, s, b, io, static_cast<uint32_t>(n), k, r);
   else

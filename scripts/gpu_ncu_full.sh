@@ -10,11 +10,16 @@ cap() {  # workload, kernel regex, skip, extra bench args
   python scripts/ncu_summary.py gpurun_out/prof_${TAG}_$w.ncu-rep > gpurun_out/${TAG}_ncu_full_$w.txt 2>/dev/null
   case " $KEEP_REP " in *" $w "*) ;; *) rm -f gpurun_out/prof_${TAG}_$w.ncu-rep ;; esac
 }
-cap c2 cartpole_step_f32_tma 2
-cap c1 cartpole_step_f32_tma 2
-cap c3_hopper reward_terminal 1
-cap c3_halfcheetah reward_terminal 1
-cap c4 charged_ball_step 1
-cap c4_rollout rollout_f32_kernel 1 --total-log2 24
-cap rollout rollout_f32_kernel 1
-cap rollout_rec rollout_f32_kernel 1
+WL=${WORKLOADS:-"c2 c1 c3_hopper c3_halfcheetah c4 c4_rollout rollout rollout_rec"}
+for w in $WL; do
+  case $w in
+    c2) cap c2 cartpole_step_f32_tma 2 ;;
+    c1) cap c1 cartpole_step_f32_small 2 ;;
+    c3_hopper) cap c3_hopper reward_terminal 1 ;;
+    c3_halfcheetah) cap c3_halfcheetah reward_terminal 1 ;;
+    c4) cap c4 charged_ball_step 1 ;;
+    c4_rollout) cap c4_rollout rollout_f32_kernel 1 --total-log2 24 ;;
+    rollout) cap rollout rollout_f32_kernel 1 ;;
+    rollout_rec) cap rollout_rec rollout_f32_kernel 1 ;;
+  esac
+done
