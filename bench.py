@@ -598,7 +598,7 @@ def run_reference(args):
         "e2e": {"value": rate, "unit": W.unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit_json_line(line)
 
 
 # ==================================================================================================
@@ -832,12 +832,37 @@ def run_ours(args):
             "value": rate1, "unit": wl.unit, "cores": 1, "kind": "port",
             "sample": f"{n_s} units x {reps} passes of the numpy oracle port (oracle/emei_oracle.py, kind={wl.cpu_kind}), {wall1:.1f} s",
         }
-    print(json.dumps(line), flush=True)
+    emit_json_line(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+# The contract is ONE JSON line on stdout.  Libraries write to the process's stdout on their own (NCCL prints its
+# version banner there with printf when NCCL_DEBUG is set in the environment), so file descriptor 1 is pointed at
+# stderr for the whole run and the JSON line alone goes to the real stdout.
+_REAL_STDOUT = None
+
+
+def capture_stdout():
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit_json_line(line):
+    data = (json.dumps(line) + "\n").encode()
+    sys.stdout.flush()
+    if _REAL_STDOUT is None:
+        sys.stdout.buffer.write(data)
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    capture_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=None)

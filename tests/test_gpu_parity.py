@@ -670,6 +670,50 @@ def test_c3_full_size_properties():
         torch.cuda.empty_cache()
 
 
+def test_c4_full_size_properties():
+    """C4: ChargedBallCentering, 2^26 envs: size-independent properties at the full batch -- a fused
+    rollout equals the same number of step calls bit for bit, statistics equal the sums of the outputs, sharded
+    init equals unsharded init, and a strided subsample follows the float64 oracle step by step."""
+    n, T = 1 << 26, 3
+    a = CB.ChargedBallCenteringEnv(num_envs=n, dtype=torch.float32)
+    a.reset(seed=1004)
+    half = CB.ChargedBallCenteringEnv(num_envs=n // 2, dtype=torch.float32, env_offset=n // 2)
+    half.reset(seed=1004)
+    for k in ("on_circle", "circle_state", "free_state"):
+        assert torch.equal(a.state[k][n // 2 :], half.state[k])
+    del half
+    g = torch.Generator(device=a.device)
+    g.manual_seed(4)
+    acts = torch.randint(0, 2, (T, n), device=a.device, generator=g, dtype=torch.uint8)
+    idx = torch.arange(0, n, 4096, device=a.device)
+    sub = {k: v[idx].cpu().numpy() for k, v in a.state.items()}
+    b = CB.ChargedBallCenteringEnv(num_envs=n, dtype=torch.float32)
+    b.state = {k: v.clone() for k, v in a.state.items()}
+    p = O.ChargedBallParams()
+    on, ci, fre = sub["on_circle"].astype(bool), sub["circle_state"].astype(np.float64), sub["free_state"].astype(np.float64)
+    a.reset_stats()
+    total = 0.0
+    for t in range(T):
+        obs, rew, done, _, _ = a.step(acts[t])
+        total += float(rew.double().sum())
+        assert not bool(done.any())  # charged_ball.py:110-111
+        # teacher-forced subsample: oracle step from the engine's own previous float32 state
+        on, ci, fre = O.charged_ball_step(on, ci, fre, O.charged_ball_force(acts[t][idx].cpu().numpy(), False, p), 1, p)
+        got = {k: v[idx].cpu().numpy() for k, v in a.state.items()}
+        agree = got["on_circle"].astype(bool) == on
+        assert agree.mean() > 0.995
+        quant = (np.spacing(np.abs(ci[:, 0]).astype(np.float32)).astype(np.float64) * (1.0 + np.abs(ci[:, 1])))[:, None]
+        ok = (np.abs(got["free_state"] - fre) <= 4.0 * (1e-6 + 1e-5 * np.abs(fre)) + quant).all(axis=1)
+        assert ok[agree].mean() > 0.999  # landings re-derive theta from asin (tested separately)
+        on, ci, fre = got["on_circle"].astype(bool), got["circle_state"].astype(np.float64), got["free_state"].astype(np.float64)
+    rs, dc = a.read_stats()
+    assert dc == 0 and abs(rs - total) < 1e-6 * abs(total)
+    out = b.rollout(T, actions=acts, record=False, auto_reset=False, max_episode_steps=0)
+    for k in ("on_circle", "circle_state", "free_state"):
+        assert torch.equal(a.state[k], b.state[k]), k
+    assert abs(float(out["stats"][0]) - total) < 1e-6 * abs(total)
+
+
 def test_empty_and_ragged_batches():
     from emei_b200 import _lib
 
@@ -917,12 +961,14 @@ def test_rollout_charged_ball_equals_step_kernel(env_id, cont):
     ("ContinuousCartPoleSwingUp-v0", True, 148 * 24 * 512 + 1234),   # > 24 chunks per SM: the TMA ring recycles its slots
     ("CartPoleSwingUp-v0", False, 148 * 26 * 512 * 2 + 77),          # uint8 actions, two laps of the ring, ragged tail
     ("BoundaryInvertedPendulumSwingUp-v0", True, 1 << 21),
-    ("CartPoleBalancing-v0", False, 513),                             # one full chunk + one env
+    ("CartPoleBalancing-v0", False, 513),                             # small-batch kernel: the SCALAR form of the arithmetic
+    ("CartPoleBalancing-v0", False, 8192 + 513),                      # smallest TMA batch: 17 chunks on 17 SMs, ragged tail
+    ("ContinuousCartPoleSwingUp-v0", True, (1 << 24) + 3),            # 222 chunks per SM: every group's ring laps 11 times
 ))
 def test_step_kernel_large_batches_equal_scalar_rollout(env_id, cont, n):
-    """The step kernel (TMA ring, packed f32x2, two envs per thread) against the scalar one-env-per-thread
-    arithmetic of the rollout kernel on the same inputs: bit for bit, at sizes that wrap the shared-memory ring,
-    with ragged tails; statistics equal the sums of the outputs."""
+    """The step kernels (TMA ring with packed f32x2 pairs; the scalar small-batch kernel below 8192 envs) against the
+    rollout kernel's one-step arithmetic (packed pairs, different pairing of envs) on the same inputs: bit for bit, at
+    sizes that wrap the per-group shared-memory rings, with ragged tails; statistics equal the sums of the outputs."""
     fr = 4
     a = E.make(env_id, num_envs=n, dtype=torch.float32, freq_rate=fr)
     b = E.make(env_id, num_envs=n, dtype=torch.float32, freq_rate=fr)
