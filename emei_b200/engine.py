@@ -9,6 +9,7 @@ HBM layout:
   outputs        : reward [B,1] (engine dtype), done uint8[B,1] viewed as torch.bool.
 """
 import ctypes
+import gc
 from typing import Optional
 
 import numpy as np
@@ -288,9 +289,9 @@ class I2PEngine:
         ptrs = (src.data_ptr(), dst.data_ptr(), obs.data_ptr(), action.data_ptr(), reward.data_ptr(), done.data_ptr(),
                 env.stats.data_ptr(), self.n, ctypes.byref(self.params))
         if noise is None:
-            env._call("emei_i2p_step", *ptrs, env._stream(), launches=2)
+            env._call("emei_i2p_step", *ptrs, env._stream())
         else:
-            env._call("emei_i2p_step_noisy", *ptrs, ctypes.byref(noise), env._stream(), launches=2)
+            env._call("emei_i2p_step_noisy", *ptrs, ctypes.byref(noise), env._stream())
         self._cur = nxt
         return obs, reward, done.view(torch.bool)
 
@@ -487,7 +488,7 @@ class HostStaging:
     so range k+1's upload and range k-1's download overlap range k's kernel, and PCIe runs in both
     directions at once.  One host synchronisation per call."""
 
-    def __init__(self, env, chunks: Optional[int] = None):
+    def __init__(self, env, chunks: Optional[int] = None, fractions=None):
         self.env = env
         n = env.num_envs
         cont = len(env.action_space.shape) > 0
@@ -502,39 +503,40 @@ class HostStaging:
         self.done_dev = torch.empty((n, 1), dtype=torch.uint8, device=dev)
         self.h2d_bytes = self.a_host.numel() * self.a_host.element_size()
         self.d2h_bytes = sum(t.numel() * t.element_size() for t in (self.obs_host, self.rew_host, self.done_host))
-        if chunks is None:
-            # measured on the B200 box (scripts/probe_step_host.py, 2^20 cart-pole envs: 1 range 0.524 ms, 2: 0.517,
-            # 4: 0.555, 8: 0.605): every range costs ~5 enqueues of host time, so ranges of ~2^19 envs, at most 16
-            chunks = min(16, max(1, n >> 19))
-        chunks = max(1, min(int(chunks), n // 131072 or 1))  # small batches: one range (latency-bound anyway)
-        edges = [round(i * n / chunks) for i in range(chunks + 1)]
-        self.ranges = [(edges[i], edges[i + 1]) for i in range(chunks) if edges[i + 1] > edges[i]]
+        if fractions is None:
+            if chunks is None:
+                # measured on the B200 box (scripts/probe_step_host.py, 2^20 cart-pole envs, graph replay): 1 range
+                # 0.523 ms, 2: 0.506, 4: 0.512, 8: 0.547 -- every extra range adds 4 DMA transfers of fixed cost, so
+                # ranges of ~2^19 envs, at most 16
+                chunks = min(16, max(1, n >> 19))
+            chunks = max(1, min(int(chunks), n // 131072 or 1))  # small batches: one range (latency-bound anyway)
+            # a short first range starts the downloads early ([0.25, 0.75] measured 0.486 ms against 0.503 for halves)
+            fractions = [1.0] if chunks == 1 else [0.5 / chunks] + [(1.0 - 0.5 / chunks) / (chunks - 1)] * (chunks - 1)
+        acc, edges = 0.0, [0]
+        for f in fractions:
+            acc += f
+            edges.append(min(n, round(acc * n)))
+        edges[-1] = n
+        self.ranges = [(edges[i], edges[i + 1]) for i in range(len(edges) - 1) if edges[i + 1] > edges[i]]
         self.streams = [torch.cuda.Stream(dev) for _ in self.ranges]
         self.done_host_u8 = self.done_host.view(torch.uint8)
+        self.use_graphs = True
+        self._capture_stream = torch.cuda.Stream(dev)
+        self._graphs, self._seen, self._keep, self._pinned_ptrs = {}, {}, {}, set()
 
-    def step(self, action):
-        env = self.env
-        eng = env._engine
-        assert eng is not None and eng.has_state, "Call reset before using step method."
-        a = torch.as_tensor(action)
-        if a.is_cuda:
-            raise TypeError("step_host takes host actions; use step() for device tensors")
-        a = a.reshape(-1)
-        if a.dtype == self.a_host.dtype and a.is_pinned() and a.is_contiguous() and a.numel() == self.a_host.numel():
-            a_src = a  # already page-locked in the wire dtype: DMA straight from the caller's buffer
-        else:
-            self.a_host.copy_(a)  # host-side cast into the pinned staging buffer (uint8 / float32)
-            a_src = self.a_host
+    # ---- one host step ---------------------------------------------------------------------------
+    def _enqueue(self, a_src):
+        """Queue the whole step on the CURRENT stream (+ one side stream per range): uploads, kernels, downloads.
+        No host synchronisation: used eagerly and under CUDA-graph capture."""
+        env, eng = self.env, self.env._engine
         cur = torch.cuda.current_stream(env.device)
         if len(self.ranges) == 1:  # small batch: latency-bound, no side streams
             self.a_dev.copy_(a_src, non_blocking=True)
             obs = eng.step_range(0, env.num_envs, self.a_dev, self.rew_dev, self.done_dev, None)
-            eng.flip()
             self.obs_host.copy_(obs, non_blocking=True)
             self.rew_host.copy_(self.rew_dev, non_blocking=True)
             self.done_host_u8.copy_(self.done_dev, non_blocking=True)
-            cur.synchronize()
-            return self.obs_host.numpy(), self.rew_host.numpy(), self.done_host.numpy(), False, {}
+            return
         start = torch.cuda.Event()
         start.record(cur)
         for (lo, hi), st in zip(self.ranges, self.streams):
@@ -545,8 +547,57 @@ class HostStaging:
                 self.obs_host[lo:hi].copy_(obs[lo:hi], non_blocking=True)
                 self.rew_host[lo:hi].copy_(self.rew_dev[lo:hi], non_blocking=True)
                 self.done_host_u8[lo:hi].copy_(self.done_dev[lo:hi], non_blocking=True)
-        eng.flip()
         for st in self.streams:
             cur.wait_stream(st)
+
+    def step(self, action):
+        """Eager the first time a (caller buffer, ping-pong parity) pair is seen; captured into a CUDA graph the
+        second time and replayed from then on: a host step is ~5 enqueues per range, and at 2^20 envs the host
+        could not queue them as fast as PCIe drains them (0.52 ms per step against 0.42 ms of copies); one graph
+        launch also lets the ranges be finer.  The graph bakes pointers in, so it is keyed by the action buffer's
+        address and the engine's current ping-pong side."""
+        env = self.env
+        eng = env._engine
+        assert eng is not None and eng.has_state, "Call reset before using step method."
+        a = torch.as_tensor(action)
+        if a.is_cuda:
+            raise TypeError("step_host takes host actions; use step() for device tensors")
+        a = a.reshape(-1)
+        if a.numel() != self.a_host.numel():
+            raise ValueError(f"step_host: expected {self.a_host.numel()} actions, got {a.numel()}")
+        ptr = a.data_ptr()
+        if a.dtype == self.a_host.dtype and a.is_contiguous() and (ptr in self._pinned_ptrs or a.is_pinned()):
+            self._pinned_ptrs.add(ptr)  # is_pinned() is a driver query: asked once per buffer
+            a_src = a  # already page-locked in the wire dtype: DMA straight from the caller's buffer
+        else:
+            self.a_host.copy_(a)  # host-side cast into the pinned staging buffer (uint8 / float32)
+            a_src = self.a_host
+        cur = torch.cuda.current_stream(env.device)
+        key = (a_src.data_ptr(), getattr(eng, "_cur", 0))
+        graph = self._graphs.get(key) if self.use_graphs else None
+        if graph is None and self.use_graphs and self._seen.get(key, 0) >= 1 and len(self._graphs) < 32:
+            graph = torch.cuda.CUDAGraph()
+            launches0 = _lib.launch_count
+            # no garbage collection inside the capture: a dead CUDAGraph (an earlier env's) destroyed mid-capture
+            # invalidates it
+            gc.collect()
+            gc_was_on = gc.isenabled()
+            gc.disable()
+            try:
+                with torch.cuda.graph(graph, stream=self._capture_stream, capture_error_mode="thread_local"):
+                    self._enqueue(a_src)
+            finally:
+                if gc_was_on:
+                    gc.enable()
+            _lib.launch_count = launches0  # capture launches nothing
+            self._graphs[key] = graph
+            self._keep[key] = a_src  # the graph reads this buffer at every replay
+        if graph is not None:
+            graph.replay()
+            _lib.launch_count += len(self.ranges)
+        else:
+            self._seen[key] = self._seen.get(key, 0) + 1
+            self._enqueue(a_src)
+        eng.flip()
         cur.synchronize()
         return self.obs_host.numpy(), self.rew_host.numpy(), self.done_host.numpy(), False, {}

@@ -162,7 +162,7 @@ typedef struct emei_i2p_params {
 /*   state_in/out [n,6] = [x, th0, th1, v, w0, w1] (qpos||qvel, angles unwrapped) ; obs_out [n,6] REQUIRED
  *   (current_obs, inverted_double_pendulum.py:56-60, precedence quirk `(th + pi) % 2 * pi - pi` replicated) ;
  *   action [n] ; reward [n], done [n] = get_batch_reward / get_batch_terminal of the variant on obs_out
- *   (:84-90,114-122,150-157,185-196) ; stats nullable double[2].  Two launches: dynamics, then the scoring kernel. */
+ *   (:84-90,114-122,150-157,185-196), fused into the step kernel ; stats nullable double[2]. */
 int emei_i2p_step_f32(const float* state_in, float* state_out, float* obs_out, const void* action, float* reward,
                       uint8_t* done, double* stats, int64_t n, const emei_i2p_params* p, emei_stream_t stream);
 int emei_i2p_step_f64(const double* state_in, double* state_out, double* obs_out, const void* action, double* reward,

@@ -773,6 +773,51 @@ def test_step_host_equals_step(env_id, n):
     assert a.read_stats()[1] == b.read_stats()[1]
 
 
+@pytest.mark.parametrize("env_id,n", (("ContinuousCartPoleSwingUp-v0", 1 << 19), ("BoundaryInvertedPendulumSwingUp-v0", 4096),
+                                      ("ChargedBallCentering-v0", 300_000)))
+def test_step_host_graph_replay_equals_step(env_id, n):
+    """step_host captures its copy / kernel / copy pipeline into a CUDA graph per (action buffer, ping-pong side) and
+    replays it: many steps from ONE pinned buffer rewritten in place, from a second buffer, with device-side step()
+    calls in between and with a set_state, must equal step() bit for bit, and the graph path must really be taken."""
+    rng = np.random.default_rng(6)
+    a = E.make(env_id, num_envs=n, dtype=torch.float32, freq_rate=2)
+    b = E.make(env_id, num_envs=n, dtype=torch.float32, freq_rate=2)
+    a.reset(seed=12)
+    b.reset(seed=12)
+    cont = len(a.action_space.shape) > 0
+    bufs = [torch.empty(n, dtype=torch.float32 if cont else torch.uint8).pin_memory() for _ in range(2)]
+
+    def draw(buf):
+        if cont:
+            lo, hi = float(a.action_space.low[0]), float(a.action_space.high[0])
+            buf.copy_(torch.as_tensor(rng.uniform(lo, hi, size=n).astype(np.float32)))
+        else:
+            buf.copy_(torch.as_tensor(rng.integers(0, 2, size=n).astype(np.uint8)))
+
+    for t in range(12):
+        buf = bufs[0] if t < 8 else bufs[1]
+        draw(buf)
+        if t == 5:  # a device-side step in between flips the ping-pong side under the staging object
+            dev_act = buf.cuda()
+            a.step(dev_act)
+            b.step(dev_act)
+        if t == 9:  # new states written into the live buffers: the captured graphs must still see them
+            st = a.state
+            st = {k: v.clone() for k, v in st.items()} if isinstance(st, dict) else st.clone()
+            a.state = st
+            b.state = st
+        o1, r1, d1, _, _ = a.step(buf.cuda())
+        o2, r2, d2, _, _ = b.step_host(buf)
+        assert np.array_equal(o1.cpu().numpy(), o2, equal_nan=True), t
+        assert np.array_equal(r1.cpu().numpy(), r2, equal_nan=True) and np.array_equal(d1.cpu().numpy(), d2), t
+    assert len(b._staging._graphs) >= 2  # replayed, not only eager
+    assert a.read_stats()[1] == b.read_stats()[1]
+    b._staging.use_graphs = False  # the eager path stays available and agrees
+    draw(bufs[0])
+    o1 = a.step(bufs[0].cuda())[0]
+    assert np.array_equal(o1.cpu().numpy(), b.step_host(bufs[0])[0], equal_nan=True)
+
+
 # ================================================================================================
 # fused T-step rollout (SURVEY 8f rank 1): zoo/util.py:33-93 batched, TimeLimit + auto-reset in-kernel
 # ================================================================================================
