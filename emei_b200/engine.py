@@ -488,6 +488,25 @@ class HostStaging:
     so range k+1's upload and range k-1's download overlap range k's kernel, and PCIe runs in both
     directions at once.  One host synchronisation per call."""
 
+    @staticmethod
+    def plan_ranges(n: int, chunks: Optional[int] = None, fractions=None):
+        """[(lo, hi), ...] tiling [0, n)."""
+        if fractions is None:
+            if chunks is None:
+                # measured on the B200 box (scripts/probe_step_host.py, 2^20 cart-pole envs, graph replay): 1 range
+                # 0.523 ms, 2: 0.506, 4: 0.512, 8: 0.547 -- every extra range adds 4 DMA transfers of fixed cost, so
+                # ranges of ~2^19 envs, at most 16
+                chunks = min(16, max(1, n >> 19))
+            chunks = max(1, min(int(chunks), n // 131072 or 1))  # small batches: one range (latency-bound anyway)
+            # a short first range starts the downloads early ([0.25, 0.75] measured 0.486 ms against 0.503 for halves)
+            fractions = [1.0] if chunks == 1 else [0.5 / chunks] + [(1.0 - 0.5 / chunks) / (chunks - 1)] * (chunks - 1)
+        acc, edges = 0.0, [0]
+        for f in fractions:
+            acc += f
+            edges.append(min(n, int(round(acc * n)) // 16 * 16))  # interior edges on 16-env boundaries: every array
+        edges[-1] = n                                             # of a range (uint8 flags included) stays 16-byte aligned
+        return [(edges[i], edges[i + 1]) for i in range(len(edges) - 1) if edges[i + 1] > edges[i]]
+
     def __init__(self, env, chunks: Optional[int] = None, fractions=None):
         self.env = env
         n = env.num_envs
@@ -503,21 +522,7 @@ class HostStaging:
         self.done_dev = torch.empty((n, 1), dtype=torch.uint8, device=dev)
         self.h2d_bytes = self.a_host.numel() * self.a_host.element_size()
         self.d2h_bytes = sum(t.numel() * t.element_size() for t in (self.obs_host, self.rew_host, self.done_host))
-        if fractions is None:
-            if chunks is None:
-                # measured on the B200 box (scripts/probe_step_host.py, 2^20 cart-pole envs, graph replay): 1 range
-                # 0.523 ms, 2: 0.506, 4: 0.512, 8: 0.547 -- every extra range adds 4 DMA transfers of fixed cost, so
-                # ranges of ~2^19 envs, at most 16
-                chunks = min(16, max(1, n >> 19))
-            chunks = max(1, min(int(chunks), n // 131072 or 1))  # small batches: one range (latency-bound anyway)
-            # a short first range starts the downloads early ([0.25, 0.75] measured 0.486 ms against 0.503 for halves)
-            fractions = [1.0] if chunks == 1 else [0.5 / chunks] + [(1.0 - 0.5 / chunks) / (chunks - 1)] * (chunks - 1)
-        acc, edges = 0.0, [0]
-        for f in fractions:
-            acc += f
-            edges.append(min(n, round(acc * n)))
-        edges[-1] = n
-        self.ranges = [(edges[i], edges[i + 1]) for i in range(len(edges) - 1) if edges[i + 1] > edges[i]]
+        self.ranges = self.plan_ranges(n, chunks, fractions)
         self.streams = [torch.cuda.Stream(dev) for _ in self.ranges]
         self.done_host_u8 = self.done_host.view(torch.uint8)
         self.use_graphs = True

@@ -316,3 +316,23 @@ def test_obs_noise_mirror_is_gaussian_and_step_keyed():
     assert abs(np.corrcoef(z[0, :, 0], z[0, :, 1])[0, 1]) < 0.03 and abs(np.corrcoef(z[0, :, 0], z[1, :, 0])[0, 1]) < 0.03
     assert not np.array_equal(z, P.obs_noise(n, 4, sig, 99, 4, 2))
     assert np.array_equal(z[:, 5000:], P.obs_noise(n - 5000, 4, sig, 99, 3, 2, env_offset=5000))
+
+
+def test_step_host_ranges_are_aligned_partitions():
+    """HostStaging cuts the batch into ranges whose interior edges sit on 16-env boundaries (every per-range pointer,
+    uint8 flags included, stays 16-byte aligned for the C ABI) and that tile [0, n) exactly."""
+    from emei_b200.engine import HostStaging
+
+    class _Space:
+        shape = (1,)
+
+    class _Env:
+        def __init__(self, n):
+            self.num_envs, self.action_space = n, _Space()
+
+    for n in (1, 4096, 300_000, 1_100_003, (1 << 23), (1 << 23) + 7, (1 << 26) + 1):
+        for chunks, fractions in ((None, None), (3, None), (None, [0.1, 0.3, 0.6])):
+            r = HostStaging.plan_ranges(n, chunks, fractions)
+            assert r[0][0] == 0 and r[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(r, r[1:])) and all(hi > lo for lo, hi in r)
+            assert all(lo % 16 == 0 for lo, _ in r)

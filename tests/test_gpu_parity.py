@@ -6,6 +6,7 @@ Tolerances (BASELINE.json north_star):
   * float32 mode: 1e-5 rel + 1e-6 abs per teacher-forced step; flags exact except where the state
     lies within tolerance of a threshold.
 """
+import math
 import warnings
 
 import numpy as np
@@ -670,6 +671,42 @@ def test_c3_full_size_properties():
         torch.cuda.empty_cache()
 
 
+@pytest.mark.parametrize("env_id,n", (("ContinuousCartPoleSwingUp-v0", 1 << 20), ("CartPoleSwingUp-v0", (1 << 21) + 5),
+                                      ("BoundaryInvertedPendulumSwingUp-v0", 4096), ("ReboundInvertedPendulumBalancing-v0", 1 << 20)))
+def test_step_mirror_symmetry_full_size(env_id, n):
+    """A size-independent property of the dynamics (cartpole.py:48-60 is odd in (x, x', theta, theta', F)): stepping
+    the mirrored batch with the mirrored actions gives the mirrored result BIT FOR BIT -- every float32 operation of
+    the kernel (packed FMAs, Cody-Waite reduction, quadrant logic, angle addition, MUFU.RCP) is sign-symmetric under
+    round-to-nearest -- with the same rewards (cos is even) and done flags.  Full BASELINE batch sizes."""
+    a = E.make(env_id, num_envs=n, dtype=torch.float32, freq_rate=4)
+    b = E.make(env_id, num_envs=n, dtype=torch.float32, freq_rate=4)
+    g = torch.Generator(device=a.device)
+    g.manual_seed(77)
+    scale = torch.tensor([4.0, 5.0, 3.14159, 8.0], device=a.device)
+    if "InvertedPendulum" in env_id:
+        scale = torch.tensor([1.9, 3.14159, 5.0, 8.0], device=a.device)
+    st = (torch.rand((n, 4), device=a.device, generator=g) * 2 - 1) * scale
+    st[: n // 16] *= 25.0  # un-wrapped angles, envs far outside the rail
+    cont = len(a.action_space.shape) > 0
+    if cont:
+        hi = float(a.action_space.high[0])
+        act = (torch.rand(n, device=a.device, generator=g) * 2 - 1) * hi
+        act_m = -act
+    else:
+        act = torch.randint(0, 2, (n,), device=a.device, generator=g, dtype=torch.uint8)
+        act_m = 1 - act
+    a.state, b.state = st, -st
+    o1, r1, d1, _, _ = a.step(act)
+    o2, r2, d2, _, _ = b.step(act_m)
+    assert torch.equal(a.state, -b.state)
+    if "InvertedPendulum" in env_id:  # the observation wraps theta into [-pi, pi): mirrored except exactly at -pi
+        inner = o1[:, 1] != -math.pi
+        assert torch.equal(o1[inner], -o2[inner])
+    else:
+        assert torch.equal(o1, -o2)
+    assert torch.equal(r1, r2) and torch.equal(d1, d2)
+
+
 def test_c4_full_size_properties():
     """C4: ChargedBallCentering, 2^26 envs: size-independent properties at the full batch -- a fused
     rollout equals the same number of step calls bit for bit, statistics equal the sums of the outputs, sharded
@@ -741,7 +778,7 @@ def test_empty_and_ragged_batches():
 # ================================================================================================
 # step_host: the end-to-end host path (chunked multi-stream pipeline) must equal step() bit for bit
 # ================================================================================================
-@pytest.mark.parametrize("n", (1000, 300_000))
+@pytest.mark.parametrize("n", (1000, 300_000, 1_100_003))  # one range, one range, two unequal ranges with a ragged end
 @pytest.mark.parametrize("env_id", ("ContinuousCartPoleSwingUp-v0", "CartPoleBalancing-v0", "BoundaryInvertedPendulumSwingUp-v0",
                                     "ChargedBallCentering-v0"))
 def test_step_host_equals_step(env_id, n):
