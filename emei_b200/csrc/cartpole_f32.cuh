@@ -1,7 +1,7 @@
-// float32 (tolerance-mode) cart-pole / analytic inverted-pendulum step: pieces shared by the step kernel
-// (cartpole_tma.cuh: TMA-staged, two envs per thread in packed f32x2 registers) and the fused rollout kernel
-// (rollout_f32.cuh: one env per thread, scalar) -- constants, action decoding, the scalar integrator, and the
-// reward / terminal / observation of one env.
+// float32 (tolerance-mode) cart-pole / analytic inverted-pendulum step: pieces shared by the step kernels
+// (cartpole_tma.cuh: TMA-staged, two envs per thread in packed f32x2 registers; the scalar small-batch kernel) and the
+// fused rollout kernel (rollout_f32.cuh: two envs per thread, packed) -- constants, action decoding, the scalar
+// form of the step, and the reward / terminal / observation of one env.
 //
 // Replaces BaseControlEnv.step (base_control.py:61-83), ODE_approximation's forward-Euler loop
 // (base_control.py:160-164), BaseCartPoleEnv._dsdt (cartpole.py:48-60) and the reward/terminal of

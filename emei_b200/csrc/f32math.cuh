@@ -1,8 +1,8 @@
 // Lean float32 math for the tolerance-mode (f32) kernels.
 //
-// The f32 kernels are bounded by warp-instruction issue, not by HBM (ncu, profiles/r01_*): CUDA's
-// sincosf + four IEEE divides cost ~135 SASS instructions per Euler sub-step.  These replacements
-// cost ~40 and stay well inside the 1e-5 rel + 1e-6 abs per-step envelope of BASELINE.json
+// CUDA's sincosf + four IEEE divides cost ~135 SASS instructions per Euler sub-step, which made the f32 step
+// issue-bound.  These replacements cost ~40 (and a sub-step after the first ~30, see cartpole_integrate) and stay
+// well inside the 1e-5 rel + 1e-6 abs per-step envelope of BASELINE.json
 // (measured by tools/f32_study, which compiles this very header for the host):
 //   * sincos: Cody-Waite 3-constant reduction to [-pi/4, pi/4] + degree-7/8 minimax polynomials
 //     (the classic single-precision kernels), quadrant fix-up with integer ops; |x| > 1e5 or
@@ -86,8 +86,8 @@ constexpr float kC0 = 4.166664568298827e-2f, kC1 = -1.388731625493765e-3f, kC2 =
 //               FFMA2 occupies the fma pipe for two cycles but the scheduler for one, so packing moves the
 //               bound from "issue slots" (~250 / env-step) to "fma-pipe cycles" (~135 / env-step).
 // Every f32x2 lane is an IEEE fma.rn / mul.rn / add.rn, so V = f2 produces exactly the bits of V = float:
-// expressions are arranged so that no negation of a packed value is needed (negated constants / negated
-// intermediates commute with round-to-nearest).
+// negations are exact (negated constants, negated intermediates and vneg() commute with round-to-nearest; ptxas
+// folds a packed vneg into the consuming FFMA2's operand modifier).
 // ---------------------------------------------------------------------------------------------
 __host__ __device__ __forceinline__ float vfma(float a, float b, float c) { return fmaf(a, b, c); }
 #if EMEI_F32_DEVICE
@@ -370,6 +370,7 @@ __host__ __device__ __forceinline__ void cartpole_substep(float& x, float& xd, f
   cartpole_euler<float>(x, xd, th, w, s, c, -f_mt, k);
 }
 #ifdef __CUDACC__
+// packed sub-step with a full sincos: the previous generation, kept for the A/B variants of tools/kbench
 __device__ __forceinline__ void cartpole_substep2(f2& x, f2& xd, f2& th, f2& w, f2 nf_mt, uint32_t flip, const CartPoleK& k) {
   f2 s, c;
   sincos_core(th, &s, &c, flip);
