@@ -219,3 +219,32 @@ def test_i2p_step_energy_and_obs_quirk():
     y2, _ = O.i2p_step(st, np.clip(rng.uniform(-2, 2, 0), -1, 1) if False else np.zeros(64), 0.02, 2, True, p)
     assert np.array_equal(obs[:, [0, 3, 4, 5]], y[:, [0, 3, 4, 5]])
     assert np.allclose(obs[:, 1:3], (y[:, 1:3] + np.pi) % 2 * np.pi - np.pi, rtol=0, atol=0)
+
+
+def test_oracle_mirror_symmetry_and_action_hold():
+    """Domain properties of the restated dynamics (cartpole.py:48-60, base_control.py:160-164): the map is odd in
+    (x, x', theta, theta', F) bit for bit (IEEE arithmetic and libm sin/cos are sign-symmetric), the force is held
+    over all sub-steps (freq_rate sub-steps of one call == freq_rate calls with freq_rate = 1), and rewards / terminals
+    are even."""
+    rng = np.random.default_rng(5)
+    n = 20000
+    st = rng.uniform(-1, 1, size=(n, 4)) * np.array([4.0, 5.0, 40.0, 8.0])
+    act = rng.uniform(-1, 1, size=(n, 1)).astype(np.float32)
+    p = O.cartpole_params("continuous_swingup")
+    f = O.cartpole_force(act, True, p)
+    a = O.cartpole_step_f64ref(st, f, 0.02, 4, p)
+    b = O.cartpole_step_f64ref(-st, -f, 0.02, 4, p)
+    assert np.array_equal(a, -b)
+    assert np.array_equal(O.cartpole_reward("swingup", a), O.cartpole_reward("swingup", b))
+    assert np.array_equal(O.cartpole_terminal("swingup", a, p), O.cartpole_terminal("swingup", b, p))
+    c = st
+    for _ in range(4):
+        c = O.cartpole_step_f64ref(c, f, 0.02, 1, p)
+    assert np.array_equal(a, c)
+    ip = O.InvertedPendulumParams()
+    ctrl = rng.uniform(-3, 3, size=n)
+    s1, o1 = O.ip_step(st[:, [0, 2, 1, 3]], ctrl, 0.02, 2, True, ip, libm=True)
+    s2, o2 = O.ip_step(-st[:, [0, 2, 1, 3]], -ctrl, 0.02, 2, True, ip, libm=True)
+    assert np.array_equal(s1, -s2)
+    # the observation's (theta + pi) % 2 pi - pi (inverted_pendulum.py:45-49) rounds differently for +theta and -theta
+    assert np.allclose(O.ip_reward("ip_boundary_swingup", o1), O.ip_reward("ip_boundary_swingup", o2), rtol=0, atol=1e-14)
