@@ -742,11 +742,17 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
         time.sleep(0.3)
-    if graph is not None:
-        graph.replay()  # warm the instantiated graph (also puts the GPU under load for the clock samples)
-    else:
-        wl.step(0)
-    torch.cuda.synchronize()
+    # warm the instantiated graph / the step, and keep the GPU under load until nvidia-smi has delivered its first
+    # samples (it needs a few hundred ms to start; a 4 ms C1 region would otherwise end before the first one)
+    t_warm = time.perf_counter()
+    while True:
+        if graph is not None:
+            graph.replay()
+        else:
+            wl.step(0)
+        torch.cuda.synchronize()
+        if rank != 0 or len(sampler.rows) >= 3 or time.perf_counter() - t_warm > 1.5:
+            break
     _lib.call("emei_stats_reset", wl.stats.data_ptr(), torch.cuda.current_stream(dev).cuda_stream, launches=0)
     launches0 = _lib.launch_count
     if world > 1:
