@@ -696,6 +696,14 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)", 1965.0
 
 
+def measured_math_peaks():
+    """FP32 / FP64 FMA and MUFU peaks measured on the box by tools/f2bench (SURVEY 8d asks for them beside hbm_gbs)."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "math_peaks.json")))
+    except Exception:
+        return None
+
+
 def measured_traffic(workload):
     """dram bytes per launch of the dominant kernel from the committed ncu --set full capture (profiles/traffic.json,
     written by scripts/make_traffic_json.py); None when there is no capture for this workload."""
@@ -855,6 +863,11 @@ def run_ours(args):
             "t_hbm_us": t_hbm * 1e6, "slower_bound": "math" if t_math > t_hbm else "hbm",
             "frac_of_slower_bound": max(t_math, t_hbm) / (kern_ms * 1e-3),
         }
+    mp = measured_math_peaks()
+    if mp is not None and ipu:
+        tgt = roofline["math"] if "math" in roofline else roofline
+        tgt["measured_math_peaks"] = {k: mp[k] for k in ("fp32_tflops", "fp64_tflops", "mufu_rcp_per_s", "mufu_sin_per_s") if k in mp}
+        tgt["measured_math_peaks"]["source"] = "profiles/math_peaks.json (tools/f2bench on the B200 box)"
     tr = measured_traffic(args.workload)
     if tr is not None:
         roofline["traffic"] = tr["bytes_per_launch"]

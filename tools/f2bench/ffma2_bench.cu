@@ -81,9 +81,38 @@ template<int MODE> void run2(const char* name, float* d, int blocks, int threads
   float ms; cudaEventElapsedTime(&ms,e0,e1);
   printf("%s: %.3f ms -> %.2f cycles per loop iteration of 4 instr per warp @1.965GHz (blocks=%d threads=%d)\n",name,ms,ms*1e-3*1.965e9/iters,blocks,threads);
 }
-int main(){ { float* d; cudaMalloc(&d,148*8*256*4);
+// ---- math peaks the rooflines refer to: FP64 FMA, MUFU (rcp / sin), I2F, measured with 8 independent chains
+// MODE 0: DFMA, 1: MUFU.RCP, 2: MUFU.SIN (via __sinf's sin.approx), 3: I2F.F32.U32
+template<int MODE> __global__ void k4(float* out, int iters, float x0){
+  double d[8]; float f[8]; unsigned u[8];
+  for(int j=0;j<8;++j){ d[j]=x0+threadIdx.x+j; f[j]=1.0f+1e-3f*(threadIdx.x+j); u[j]=threadIdx.x*7+j; }
+  for(int i=0;i<iters;++i){
+    #pragma unroll
+    for(int j=0;j<8;++j){
+      if (MODE==0) d[j]=fma(d[j],0.999,0.001);
+      if (MODE==1) { asm volatile("rcp.approx.ftz.f32 %0, %0;":"+f"(f[j])); f[j]+=0.5f; }  // (rcp(rcp(x)) alone is folded away)
+      if (MODE==2) asm volatile("sin.approx.ftz.f32 %0, %0;":"+f"(f[j]));
+      if (MODE==3){ float t; asm volatile("cvt.rn.f32.u32 %0, %1;":"=f"(t):"r"(u[j])); u[j]=__float_as_uint(t)>>3; }
+    }
+  }
+  float s=0; for(int j=0;j<8;++j) s+=(float)d[j]+f[j]+(float)u[j];
+  out[blockIdx.x*blockDim.x+threadIdx.x]=s;
+}
+template<int MODE> double run4(const char* name, float* d){
+  int iters=4000; cudaEvent_t e0,e1; cudaEventCreate(&e0);cudaEventCreate(&e1);
+  k4<MODE><<<148*8,256>>>(d,50,1.f); cudaDeviceSynchronize();
+  cudaEventRecord(e0); k4<MODE><<<148*8,256>>>(d,iters,1.f); cudaEventRecord(e1); cudaDeviceSynchronize();
+  float ms; cudaEventElapsedTime(&ms,e0,e1);
+  double ops=(double)148*8*256*iters*8, rate=ops/(ms*1e-3);
+  printf("%s: %.3f ms -> %.3f T lane-ops/s, %.1f lanes per SM per clk @1.965GHz\n",name,ms,rate/1e12,rate/148/1.965e9);
+  return rate;
+}
+int main(int argc, char** argv){ { float* d; cudaMalloc(&d,148*8*256*4);
   run3<0>("FFMA2, 3 distinct reg operands, 8 warps/SMSP",d); run3<1>("FFMA, 3 distinct reg operands, 8 warps/SMSP",d);
   run2<0>("FMUL2 x4 indep, 8 CTAs/SM",d,148*8,256); run2<1>("FADD2 x4 indep, 8 CTAs/SM",d,148*8,256);
   run2<2>("FFMA2 chain, 1 warp/SMSP",d,148,128); run2<3>("FFMA chain, 1 warp/SMSP",d,148,128);
   run2<2>("FFMA2 chain, 4 warps/SMSP",d,148,512); run2<3>("FFMA chain, 4 warps/SMSP",d,148,512);
-  run2<2>("FFMA2 chain, 8 warps/SMSP",d,148,1024); } float* d; cudaMalloc(&d,148*8*256*4); run<0>("FFMA scalar",d,8); run<1>("FFMA2 packed",d,8); run<2>("FFMA2 + 1:1 ALU",d,8); return 0; }
+  run2<2>("FFMA2 chain, 8 warps/SMSP",d,148,1024); } float* d; cudaMalloc(&d,148*8*256*4); run<0>("FFMA scalar",d,8); run<1>("FFMA2 packed",d,8); run<2>("FFMA2 + 1:1 ALU",d,8);
+  double dfma=run4<0>("DFMA (FP64), 8 chains",d), rcp=run4<1>("MUFU.RCP, 8 chains",d), sn=run4<2>("MUFU.SIN, 8 chains",d), i2f=run4<3>("I2F.F32.U32, 8 chains",d);
+  if (argc > 1) { FILE* f=fopen(argv[1],"w"); if (f) { fprintf(f,"{\n \"fp64_fma_lane_ops_per_s\": %.4e,\n \"fp64_tflops\": %.2f,\n \"mufu_rcp_per_s\": %.4e,\n \"mufu_sin_per_s\": %.4e,\n \"i2f_per_s\": %.4e,\n \"how\": \"tools/f2bench/ffma2_bench: 148*8 CTAs x 256 threads, 8 independent chains per thread, CUDA events, natural clocks\"\n}\n", dfma, 2*dfma/1e12, rcp, sn, i2f); fclose(f);} }
+  return 0; }
