@@ -391,7 +391,7 @@ class ChargedBall(Workload):
 
     key, metric, unit = "c4", "env_steps_per_sec", "env-steps/s"
     name = "ChargedBallCentering batched step, 2^26 envs total sharded over the ranks, freq_rate=1, float32 (BASELINE configs[3])"
-    kernel = "emei::charged_ball_step_kernel<float>"
+    kernel = "emei::charged_ball_step_f32_kernel<AK=u8>"
     scaling, use_graph = "strong", False
     total = 1 << 26
     alg_bytes = 56  # state in 25 + action 1 (uint8) + state out 25 + reward 4 + done 1
@@ -487,7 +487,7 @@ class CartPoleRollout(Workload):
 
     key, metric, unit = "rollout", "env_steps_per_sec", "env-steps/s"
     name = "ContinuousCartPoleSwingUp fused rollout, 2^20 envs/GPU x horizon steps per launch, freq_rate=4, in-kernel random policy + TimeLimit(1000) + auto-reset, float32 (SURVEY 8f rank 1)"
-    kernel = "emei::cartpole_rollout_f32_kernel<IP=0, AK=f32, FR=4, RECORD=0>"
+    kernel = "emei::rollout_f32_kernel<CartPoleDyn<IP=0, AK=f32, FR=4>, RECORD=0>"
     env_id, n_envs, freq_rate = "ContinuousCartPoleSwingUp-v0", 1 << 20, 4
     use_graph, bound = False, "issue"
     record = False
@@ -539,7 +539,7 @@ class CartPoleRolloutRecord(CartPoleRollout):
 
     key = "rollout_rec"
     name = CartPoleRollout.name.replace("fused rollout", "fused rollout + transition records (dataset layout)")
-    kernel = "emei::cartpole_rollout_f32_kernel<IP=0, AK=f32, FR=4, RECORD=1>"
+    kernel = "emei::rollout_f32_kernel<CartPoleDyn<IP=0, AK=f32, FR=4>, RECORD=1>"
     record = True
     inst_per_unit = 289.9  # (ncu, profiles/r01_launches_rollout_rec.csv) t_issue = 0.26 ms > t_hbm = 0.22 ms (42 B/env-step) at 2^25 env-steps per launch: still issue-bound
 
