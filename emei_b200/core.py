@@ -259,8 +259,8 @@ class EmeiEnv(Freezable):
         staging buffers (valid until the next ``step_host``)."""
         from .engine import HostStaging
 
-        if getattr(self, "_obs_noise_on", lambda: False)():
-            raise NotImplementedError("obs_noise_params != 0 is implemented for step() only")
+        if getattr(self, "_obs_noise_on", lambda: False)() and not hasattr(self._engine, "step_range"):
+            raise NotImplementedError("obs_noise_params != 0 with step_host: inverted pendulum only (emei_ip_step_noisy)")
         if getattr(self, "_staging", None) is None:
             self._staging = HostStaging(self)
         return self._staging.step(action)

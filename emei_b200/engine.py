@@ -186,9 +186,11 @@ class CartPoleEngine(RolloutMixin):
         self._cur = nxt
         return (obs if obs is not None else dst), reward, done.view(torch.bool)
 
-    def step_range(self, lo: int, hi: int, action: torch.Tensor, reward: torch.Tensor, done: torch.Tensor, obs_out):
+    def step_range(self, lo: int, hi: int, action: torch.Tensor, reward: torch.Tensor, done: torch.Tensor, obs_out,
+                   noise: Optional[_lib.NoiseParams] = None):
         """Launch the step kernel for envs [lo, hi) only (src -> dst of the CURRENT ping-pong pair, no flip):
-        the building block of the chunked host pipeline.  Call ``flip()`` once all ranges are launched."""
+        the building block of the chunked host pipeline.  Call ``flip()`` once all ranges are launched.
+        ``noise``: the step's NoiseParams (obs_noise_params); the range draws the streams of its own global env ids."""
         env = self.env
         self._alloc()
         src, dst = self._bufs[self._cur], self._bufs[1 - self._cur]
@@ -196,13 +198,17 @@ class CartPoleEngine(RolloutMixin):
             obs_out = self._obs[1 - self._cur]
         self.params.action_kind = _ACTION_KIND[action.dtype]
         es, ea = src.element_size() * 4, action.element_size()
-        env._call(
-            "emei_cartpole_step",
-            src.data_ptr() + lo * es, dst.data_ptr() + lo * es,
-            (obs_out.data_ptr() + lo * es) if obs_out is not None else None, action.data_ptr() + lo * ea,
-            reward.data_ptr() + lo * reward.element_size(), done.data_ptr() + lo, env.stats.data_ptr(), hi - lo,
-            ctypes.byref(self.params), env._stream(),
-        )
+        ptrs = (src.data_ptr() + lo * es, dst.data_ptr() + lo * es,
+                (obs_out.data_ptr() + lo * es) if obs_out is not None else None, action.data_ptr() + lo * ea,
+                reward.data_ptr() + lo * reward.element_size(), done.data_ptr() + lo, env.stats.data_ptr(), hi - lo,
+                ctypes.byref(self.params))
+        if noise is None:
+            env._call("emei_cartpole_step", *ptrs, env._stream())
+        else:
+            z = _lib.NoiseParams()
+            ctypes.memmove(ctypes.byref(z), ctypes.byref(noise), ctypes.sizeof(z))
+            z.env_offset = noise.env_offset + lo
+            env._call("emei_ip_step_noisy", *ptrs, ctypes.byref(z), env._stream())
         return obs_out if obs_out is not None else dst
 
     def flip(self):
@@ -530,14 +536,15 @@ class HostStaging:
         self._graphs, self._seen, self._keep, self._pinned_ptrs = {}, {}, {}, set()
 
     # ---- one host step ---------------------------------------------------------------------------
-    def _enqueue(self, a_src):
+    def _enqueue(self, a_src, noise=None):
         """Queue the whole step on the CURRENT stream (+ one side stream per range): uploads, kernels, downloads.
         No host synchronisation: used eagerly and under CUDA-graph capture."""
         env, eng = self.env, self.env._engine
         cur = torch.cuda.current_stream(env.device)
+        kw = {} if noise is None else {"noise": noise}
         if len(self.ranges) == 1:  # small batch: latency-bound, no side streams
             self.a_dev.copy_(a_src, non_blocking=True)
-            obs = eng.step_range(0, env.num_envs, self.a_dev, self.rew_dev, self.done_dev, None)
+            obs = eng.step_range(0, env.num_envs, self.a_dev, self.rew_dev, self.done_dev, None, **kw)
             self.obs_host.copy_(obs, non_blocking=True)
             self.rew_host.copy_(self.rew_dev, non_blocking=True)
             self.done_host_u8.copy_(self.done_dev, non_blocking=True)
@@ -548,7 +555,7 @@ class HostStaging:
             with torch.cuda.stream(st):
                 st.wait_event(start)  # everything queued before this call (reset, set_state, ...) is visible
                 self.a_dev[lo:hi].copy_(a_src[lo:hi], non_blocking=True)
-                obs = eng.step_range(lo, hi, self.a_dev, self.rew_dev, self.done_dev, None)
+                obs = eng.step_range(lo, hi, self.a_dev, self.rew_dev, self.done_dev, None, **kw)
                 self.obs_host[lo:hi].copy_(obs[lo:hi], non_blocking=True)
                 self.rew_host[lo:hi].copy_(self.rew_dev[lo:hi], non_blocking=True)
                 self.done_host_u8[lo:hi].copy_(self.done_dev[lo:hi], non_blocking=True)
@@ -578,6 +585,12 @@ class HostStaging:
             self.a_host.copy_(a)  # host-side cast into the pinned staging buffer (uint8 / float32)
             a_src = self.a_host
         cur = torch.cuda.current_stream(env.device)
+        noise = getattr(env, "_next_obs_noise", lambda: None)()
+        if noise is not None:  # obs_noise_params: the step counter changes every call, so nothing can be baked into a graph
+            self._enqueue(a_src, noise)
+            eng.flip()
+            cur.synchronize()
+            return self.obs_host.numpy(), self.rew_host.numpy(), self.done_host.numpy(), False, {}
         key = (a_src.data_ptr(), getattr(eng, "_cur", 0))
         graph = self._graphs.get(key) if self.use_graphs else None
         if graph is None and self.use_graphs and self._seen.get(key, 0) >= 1 and len(self._graphs) < 32:

@@ -1263,6 +1263,17 @@ def test_ip_obs_noise_vs_oracle_and_philox_mirror(dtype, fr):
     assert torch.equal(half.state, full.state[n // 2 :])
     with pytest.raises(NotImplementedError):
         full.rollout(4)
+    # the host path draws the same noise (ranges keyed by their global env ids, no graph replay with a moving counter)
+    h = E.make(IP[kind], freq_rate=fr, num_envs=n, dtype=dtype, obs_noise_params=(0.01, 0.03))
+    g = E.make(IP[kind], freq_rate=fr, num_envs=n, dtype=dtype, obs_noise_params=(0.01, 0.03))
+    h.reset(seed=11)
+    g.reset(seed=11)
+    h.state, g.state = st, st
+    for _ in range(3):
+        o1 = g.step(act)[0]
+        o2 = h.step_host(act[:, 0])[0]
+        assert np.array_equal(o1.cpu().numpy(), o2)
+    assert torch.equal(h.state, g.state)
 
 
 def test_obs_noise_forms_moments_and_i2p():
@@ -1300,3 +1311,20 @@ def test_obs_noise_forms_moments_and_i2p():
     e1 = E.make(I2P["i2p_boundary_swingup"], freq_rate=2, num_envs=m, dtype=torch.float64)
     e0.state, e1.state = st6, st6
     assert torch.equal(e0.step(act6)[0], e1.step(act6)[0])
+
+
+def test_obs_noise_step_host_multi_range():
+    """step_host with obs_noise_params at a size that is cut into two ranges: every range must draw the streams of its
+    own global env ids (NoiseParams.env_offset + lo), i.e. equal the single-launch step() bit for bit."""
+    n = (1 << 20) + 48
+    st, act = ip_inputs(4004, n)
+    a = E.make(IP["ip_rebound_swingup"], num_envs=n, dtype=torch.float32, obs_noise_params=0.02)
+    b = E.make(IP["ip_rebound_swingup"], num_envs=n, dtype=torch.float32, obs_noise_params=0.02)
+    a.reset(seed=2)
+    b.reset(seed=2)
+    a.state, b.state = st, st
+    for _ in range(2):
+        o1, r1, d1, _, _ = a.step(act)
+        o2, r2, d2, _, _ = b.step_host(act[:, 0])
+        assert np.array_equal(o1.cpu().numpy(), o2) and np.array_equal(r1.cpu().numpy(), r2) and np.array_equal(d1.cpu().numpy(), d2)
+    assert len(b._staging.ranges) == 2 and not b._staging._graphs
