@@ -533,7 +533,7 @@ class HostStaging:
         self.done_host_u8 = self.done_host.view(torch.uint8)
         self.use_graphs = True
         self._capture_stream = torch.cuda.Stream(dev)
-        self._graphs, self._seen, self._keep, self._pinned_ptrs = {}, {}, {}, set()
+        self._graphs, self._seen, self._keep, self._pinned = {}, {}, {}, {}
 
     # ---- one host step ---------------------------------------------------------------------------
     def _enqueue(self, a_src, noise=None):
@@ -578,8 +578,11 @@ class HostStaging:
         if a.numel() != self.a_host.numel():
             raise ValueError(f"step_host: expected {self.a_host.numel()} actions, got {a.numel()}")
         ptr = a.data_ptr()
-        if a.dtype == self.a_host.dtype and a.is_contiguous() and (ptr in self._pinned_ptrs or a.is_pinned()):
-            self._pinned_ptrs.add(ptr)  # is_pinned() is a driver query: asked once per buffer
+        if a.dtype == self.a_host.dtype and a.is_contiguous() and (ptr in self._pinned or a.is_pinned()):
+            # is_pinned() is a driver query: asked once per buffer.  The cache keeps the tensor alive, so its address
+            # cannot be handed to a pageable allocation while it is trusted (at most 32 caller buffers are remembered).
+            if ptr not in self._pinned and len(self._pinned) < 32:
+                self._pinned[ptr] = a
             a_src = a  # already page-locked in the wire dtype: DMA straight from the caller's buffer
         else:
             self.a_host.copy_(a)  # host-side cast into the pinned staging buffer (uint8 / float32)
@@ -614,6 +617,8 @@ class HostStaging:
             graph.replay()
             _lib.launch_count += len(self.ranges)
         else:
+            if len(self._seen) > 256:  # a caller that never reuses a buffer: nothing worth remembering
+                self._seen.clear()
             self._seen[key] = self._seen.get(key, 0) + 1
             self._enqueue(a_src)
         eng.flip()
