@@ -751,6 +751,30 @@ def test_c4_full_size_properties():
     assert abs(float(out["stats"][0]) - total) < 1e-6 * abs(total)
 
 
+def test_c5_freeze_unfreeze_full_size():
+    """C5's freeze / unfreeze at its per-GPU size (2^26 cart-pole envs): freeze -> steps -> unfreeze restores
+    the state bit for bit (core.py:18-37, base_control.py:32-36), a second freeze overwrites the snapshot, and stepping
+    after the restore reproduces the first trajectory."""
+    n = 1 << 26
+    env = CP.CartPoleSwingUpEnv(num_envs=n, dtype=torch.float32, freq_rate=1)
+    env.reset(seed=1005)
+    g = torch.Generator(device=env.device)
+    g.manual_seed(9)
+    act = torch.randint(0, 2, (n,), device=env.device, generator=g, dtype=torch.uint8)
+    s0 = env.state.clone()
+    env.freeze()
+    o1 = env.step(act)[0].clone()
+    env.step(act)
+    env.unfreeze()
+    assert torch.equal(env.state, s0)
+    assert torch.equal(env.step(act)[0], o1)
+    env.freeze()  # snapshot of the stepped state replaces the old one
+    s1 = env.state.clone()
+    env.step(act)
+    env.unfreeze()
+    assert torch.equal(env.state, s1) and not torch.equal(s1, s0)
+
+
 def test_empty_and_ragged_batches():
     from emei_b200 import _lib
 
