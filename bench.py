@@ -93,22 +93,50 @@ def synth_scoring(n, family, seed=1003):
 # cpu_baseline / --impl reference are the ONLY product-side users of oracle/ (as the thing timed
 # beside the GPU path, never inside it).
 # ==================================================================================================
+def cpu_port_name():
+    """Which restatement the CPU legs time: the plain-C one (oracle/emei_oracle_c.c, built by build()) where it covers
+    the workload and its library is present, else the numpy one."""
+    try:
+        from oracle import c_oracle as C
+
+        return "C" if C.available() else "numpy"
+    except Exception:
+        return "numpy"
+
+
+def cpu_port_desc(kind):
+    if cpu_port_name() == "C" and kind in ("c2", "c1", "c3_hopper", "c3_halfcheetah"):
+        return f"plain-C oracle port (oracle/emei_oracle_c.c, kind={kind})"
+    return f"numpy oracle port (oracle/emei_oracle.py, kind={kind})"
+
+
 def _cpu_worker(args):
     kind, arrays, reps = args
     from oracle import emei_oracle as O
+
+    C = None
+    if cpu_port_name() == "C":
+        from oracle import c_oracle as C
 
     t0 = time.perf_counter()
     for _ in range(reps):
         if kind == "c2":
             st, act = arrays
             p = O.cartpole_params("continuous_swingup")
+            if C is not None:
+                nxt = C.cartpole_step_f64ref(st, O.cartpole_force(act, True, p), DT, 4, p)
+                C.cartpole_reward_terminal("continuous_swingup", nxt, p)
+                continue
             nxt = O.cartpole_step_f64ref(st, O.cartpole_force(act, True, p), DT, 4, p, libm=False)
             O.cartpole_reward("continuous_swingup", nxt)
             O.cartpole_terminal("continuous_swingup", nxt, p)
         elif kind == "c1":
             st, act = arrays
             p = O.InvertedPendulumParams()
-            nxt, obs = O.ip_step(st, act[:, 0].astype(np.float64), DT, 1, True, p)
+            if C is not None:
+                nxt, obs = C.ip_step(st, np.clip(act[:, 0].astype(np.float64), p.ctrl_low, p.ctrl_high), DT, 1, True, p)
+            else:
+                nxt, obs = O.ip_step(st, act[:, 0].astype(np.float64), DT, 1, True, p)
             O.ip_reward("ip_boundary_swingup", obs)
             O.ip_terminal("ip_boundary_swingup", obs, p)
         elif kind == "i2p":
@@ -120,11 +148,17 @@ def _cpu_worker(args):
         elif kind == "c3_hopper":
             obs, pre, act = arrays
             p = O.HopperParams(terminate_when_unhealthy=False)
+            if C is not None:
+                C.hopper_reward_terminal(obs, pre, act, p)
+                continue
             O.hopper_reward(obs, pre, act, p)
             O.hopper_terminal(obs, p)
         elif kind == "c3_halfcheetah":
             obs, pre, act = arrays
             p = O.HalfCheetahParams()
+            if C is not None:
+                C.halfcheetah_reward_terminal(obs, pre, act, p)
+                continue
             O.halfcheetah_reward(obs, pre, act, p)
             O.halfcheetah_terminal(obs)
         elif kind == "c4":
@@ -159,10 +193,23 @@ def _cpu_inputs(kind, n):
     raise ValueError(kind)
 
 
+_CPU_CHUNKS = None
+
+
+def _cpu_worker_indexed(i):
+    return _cpu_worker(_CPU_CHUNKS[i])
+
+
+def _cpu_worker_warm(i):
+    kind, arrays, _ = _CPU_CHUNKS[i]
+    return _cpu_worker((kind, [a[:256] for a in arrays], 1))
+
+
 def cpu_rate(kind, sample_units, reps, cores):
     """units/s of the oracle port: `cores` processes, each owning sample_units/cores units."""
     import multiprocessing as mp
 
+    global _CPU_CHUNKS
     arrays = _cpu_inputs(kind, sample_units)
     chunks = [(kind, [a[i::cores].copy() for a in arrays], reps) for i in range(cores)]
     with np.errstate(all="ignore"):
@@ -171,11 +218,15 @@ def cpu_rate(kind, sample_units, reps, cores):
             _cpu_worker(chunks[0])
             wall = time.perf_counter() - t0
         else:
+            # the workers are forked AFTER the inputs exist and inherit them (copy-on-write): the timed map ships only
+            # an index, not gigabytes of pickled arrays, so the CPU arm is timed on its arithmetic
+            _CPU_CHUNKS = chunks
             with mp.get_context("fork").Pool(cores) as pool:
-                pool.map(_cpu_worker, [(kind, [a[:256] for a in c[1]], 1) for c in chunks])  # spin the workers up
+                pool.map(_cpu_worker_warm, range(cores))  # spin the workers up, touch the inherited pages
                 t0 = time.perf_counter()
-                pool.map(_cpu_worker, chunks)
+                pool.map(_cpu_worker_indexed, range(cores))
                 wall = time.perf_counter() - t0
+            _CPU_CHUNKS = None
     return sample_units * reps / wall, wall
 
 
@@ -629,7 +680,7 @@ def run_reference(args):
     if args.warmup:
         cpu_rate(kind, sample, args.warmup, cores)
     rate, wall = cpu_rate(kind, sample, args.steps, cores)
-    desc = f"{sample} units/step x {args.steps} steps of the numpy oracle port (oracle/emei_oracle.py, kind={kind}), {cores} processes"
+    desc = f"{sample} units/step x {args.steps} steps of the {cpu_port_desc(kind)}, {cores} processes"
     line = {
         "impl": "reference", "metric": W.metric, "value": rate, "unit": W.unit, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps, "higher_is_better": True, "scaling": W.scaling,
@@ -894,7 +945,7 @@ def run_ours(args):
         rate1, wall1 = cpu_rate(wl.cpu_kind, n_s, reps, 1)
         line["cpu_baseline"] = {
             "value": rate1, "unit": wl.unit, "cores": 1, "kind": "port",
-            "sample": f"{n_s} units x {reps} passes of the numpy oracle port (oracle/emei_oracle.py, kind={wl.cpu_kind}), {wall1:.1f} s",
+            "sample": f"{n_s} units x {reps} passes of the {cpu_port_desc(wl.cpu_kind)}, {wall1:.1f} s",
         }
     emit_json_line(line)
     if world > 1:
