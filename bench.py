@@ -105,7 +105,7 @@ def cpu_port_name():
 
 
 def cpu_port_desc(kind):
-    if cpu_port_name() == "C" and kind in ("c2", "c1", "c3_hopper", "c3_halfcheetah"):
+    if cpu_port_name() == "C" and kind in ("c2", "c1", "c3_hopper", "c3_halfcheetah", "c4"):
         return f"plain-C oracle port (oracle/emei_oracle_c.c, kind={kind})"
     return f"numpy oracle port (oracle/emei_oracle.py, kind={kind})"
 
@@ -164,6 +164,10 @@ def _cpu_worker(args):
         elif kind == "c4":
             on, ci, fr, act = arrays
             p = O.ChargedBallParams()
+            if C is not None:
+                on, ci, fr = C.charged_ball_step(on, ci, fr, O.charged_ball_force(act, False, p), 1, p)
+                C.charged_ball_reward(fr, p)
+                continue
             on, ci, fr = O.charged_ball_step(on, ci, fr, O.charged_ball_force(act, False, p), 1, p)
             O.charged_ball_reward(fr, p)
         else:

@@ -34,6 +34,10 @@ def _load():
         lib.oc_sumsq.restype = c_double
         lib.oc_hopper_reward_terminal.argtypes = [c_int64, dp, dp] + [c_double] * 4 + [c_int] + [c_double] * 5 + [dp, bp]
         lib.oc_halfcheetah_reward_terminal.argtypes = [c_int64, dp, dp] + [c_double] * 4 + [dp, bp]
+        lib.oc_charged_ball_step.argtypes = [c_int64, bp, dp, dp, dp, c_int] + [c_double] * 4 + [c_int]
+        lib.oc_charged_ball_step.restype = None
+        lib.oc_charged_ball_reward.argtypes = [c_int64, dp, c_double, dp]
+        lib.oc_charged_ball_reward.restype = None
         for f in ("oc_cartpole_step_f64ref", "oc_cartpole_reward_terminal", "oc_ip_step", "oc_hopper_reward_terminal", "oc_halfcheetah_reward_terminal"):
             getattr(lib, f).restype = None
         _lib = lib
@@ -99,3 +103,22 @@ def halfcheetah_reward_terminal(obs, pre_obs, action, p: O.HalfCheetahParams, su
     r, d = np.empty(o.shape[0]), np.empty(o.shape[0], dtype=np.uint8)
     _load().oc_halfcheetah_reward_terminal(o.shape[0], _p(o), _p(q), ss, p.forward_reward_weight, p.ctrl_cost_weight, p.dt, _p(r), _p(d, c_uint8))
     return r.reshape(-1, 1), d.astype(bool).reshape(-1, 1)
+
+
+def charged_ball_step(on_circle, circle, free, e_force, freq_rate, p: O.ChargedBallParams, f32_force=False):
+    """charged_ball.py:25-82 (oracle/emei_oracle.py charged_ball_step, float64, libm=True) -> (on, circle, free)."""
+    lib = _load()
+    on = np.ascontiguousarray(np.asarray(on_circle).astype(np.uint8))
+    ci, fr = _d(circle).copy(), _d(free).copy()
+    e = _d(np.asarray(e_force).reshape(-1))
+    lib.oc_charged_ball_step(on.shape[0], _p(on, c_uint8), _p(ci), _p(fr), _p(e), int(freq_rate), p.gravity_acc, p.mass_ball, p.radius,
+                             p.time_step, int(bool(f32_force)))
+    return on.astype(bool), ci, fr
+
+
+def charged_ball_reward(free, p: O.ChargedBallParams):
+    lib = _load()
+    f = _d(free)
+    r = np.empty(f.shape[0])
+    lib.oc_charged_ball_reward(f.shape[0], _p(f), p.radius, _p(r))
+    return r.reshape(-1, 1)

@@ -93,3 +93,21 @@ def test_c_ip_step_equals_numpy_restatement():
             s2, o2 = C.ip_step(st, ctrl, 0.02, fr, swingup, p)
             assert np.array_equal(s1, s2) and np.array_equal(o1, o2)
             assert np.all((o2[:, 1] >= -np.pi) & (o2[:, 1] < np.pi))
+
+
+@pytest.mark.parametrize("tag", ("disc_fr1", "disc_fr3", "cont_fr1", "cont_fr3"))
+def test_c_charged_ball_teacher_forced_bit_exact(golden, tag):
+    """charged_ball.py:25-82 driven step by step from the executed reference's own states: regime flags, circle and free
+    states bit for bit, both regimes and landings exercised; the continuous variant's float32 force arithmetic
+    (NEP 50) included."""
+    c = golden("charged_ball")
+    p = O.ChargedBallParams()
+    fr, cont = int(tag[-1]), tag.startswith("cont")
+    on, ci, fre, act = c[tag + "_on"], c[tag + "_circle"], c[tag + "_free"], c[tag + "_action"]
+    landed = 0
+    for t in range(act.shape[0]):
+        o2, c2, f2 = C.charged_ball_step(on[t], ci[t], fre[t], O.charged_ball_force(act[t], cont, p), fr, p, f32_force=cont)
+        assert np.array_equal(o2, on[t + 1]) and np.array_equal(f2, fre[t + 1]) and np.array_equal(c2, ci[t + 1])
+        landed += int((o2 & ~on[t].astype(bool)).sum())
+    assert landed > 0
+    assert np.array_equal(C.charged_ball_reward(c["reward_free"], p)[:, 0], c["reward"])
