@@ -945,7 +945,9 @@ def run_ours(args):
     # ---------------- CPU baseline on this box's host cores (bounded sample; oracle = the thing timed beside us)
     if world == 1 and not args.no_cpu:
         n_s = wl.cpu_sample
-        reps = 8 if wl.cpu_kind in ("c2", "c1") else 2
+        # a bounded sample worth ~10 s of one core: calibrate with one pass, then size the pass count
+        _, wall0 = cpu_rate(wl.cpu_kind, n_s, 1, 1)
+        reps = int(max(2, min(200, round(10.0 / max(wall0, 1e-3)))))
         rate1, wall1 = cpu_rate(wl.cpu_kind, n_s, reps, 1)
         line["cpu_baseline"] = {
             "value": rate1, "unit": wl.unit, "cores": 1, "kind": "port",
