@@ -105,7 +105,7 @@ def cpu_port_name():
 
 
 def cpu_port_desc(kind):
-    if cpu_port_name() == "C" and kind in ("c2", "c1", "c3_hopper", "c3_halfcheetah", "c4"):
+    if cpu_port_name() == "C" and kind in ("c2", "c1", "i2p", "c3_hopper", "c3_halfcheetah", "c4"):
         return f"plain-C oracle port (oracle/emei_oracle_c.c, kind={kind})"
     return f"numpy oracle port (oracle/emei_oracle.py, kind={kind})"
 
@@ -142,7 +142,10 @@ def _cpu_worker(args):
         elif kind == "i2p":
             st, act = arrays
             p = O.I2PParams()
-            nxt, obs = O.i2p_step(st, act[:, 0].astype(np.float64), DT, 1, True, p)
+            if C is not None:
+                nxt, obs = C.i2p_step(st, act[:, 0].astype(np.float64), DT, 1, True, p)
+            else:
+                nxt, obs = O.i2p_step(st, act[:, 0].astype(np.float64), DT, 1, True, p)
             O.i2p_reward("i2p_boundary_swingup", obs)
             O.i2p_terminal("i2p_boundary_swingup", obs)
         elif kind == "c3_hopper":

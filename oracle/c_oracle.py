@@ -38,6 +38,8 @@ def _load():
         lib.oc_charged_ball_step.restype = None
         lib.oc_charged_ball_reward.argtypes = [c_int64, dp, c_double, dp]
         lib.oc_charged_ball_reward.restype = None
+        lib.oc_i2p_step.argtypes = [c_int64, dp, dp, c_double, c_int, c_int, dp, dp, dp]
+        lib.oc_i2p_step.restype = None
         for f in ("oc_cartpole_step_f64ref", "oc_cartpole_reward_terminal", "oc_ip_step", "oc_hopper_reward_terminal", "oc_halfcheetah_reward_terminal"):
             getattr(lib, f).restype = None
         _lib = lib
@@ -122,3 +124,12 @@ def charged_ball_reward(free, p: O.ChargedBallParams):
     r = np.empty(f.shape[0])
     lib.oc_charged_ball_reward(f.shape[0], _p(f), p.radius, _p(r))
     return r.reshape(-1, 1)
+
+
+def i2p_step(state, ctrl, h, freq_rate, swingup, p: O.I2PParams):
+    """oracle/emei_oracle.py i2p_step (float64, libm=True): lagrange_eqs.py:12-60 cartpole(2) + mujoco_env.py:91-97."""
+    s, c = _d(state), _d(np.asarray(ctrl).reshape(-1))
+    out, obs = np.empty_like(s), np.empty_like(s)
+    par = _d([p.mass_cart, p.mass_pole0, p.mass_pole1, p.length0, p.length1, p.gravity, p.gear, p.ctrl_low, p.ctrl_high])
+    _load().oc_i2p_step(s.shape[0], _p(s), _p(c), float(h), int(freq_rate), int(bool(swingup)), _p(par), _p(out), _p(obs))
+    return out, obs
