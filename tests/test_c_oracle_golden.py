@@ -127,3 +127,36 @@ def test_c_i2p_step_equals_numpy_restatement():
             s1, o1 = O.i2p_step(st, ctrl, 0.02, fr, swingup, p, libm=True)
             s2, o2 = C.i2p_step(st, ctrl, 0.02, fr, swingup, p)
             assert np.array_equal(s1, s2) and np.array_equal(o1, o2)
+
+
+def test_c_and_numpy_restatements_agree_on_edge_inputs():
+    """Empty batches, NaN / Inf states, thresholds hit exactly: the two restatements agree bit for bit (NaN == NaN)."""
+    p = O.cartpole_params("swingup")
+    assert C.cartpole_step_f64ref(np.zeros((0, 4)), np.zeros(0), 0.02, 4, p).shape == (0, 4)
+    r, d = C.cartpole_reward_terminal("swingup", np.zeros((0, 4)), p)
+    assert r.shape == (0, 1) and d.shape == (0, 1)
+    st = np.array([[np.nan, 0, 0, 0], [0, np.inf, 0.1, 0], [5.0, 0, 0, 0], [-5.0, 0, 0, 0], [4.999999999, 1, np.pi, -3],
+                   [0, 0, 1e6, 1e3], [0, 0, -np.inf, 0], [0, 0, 0, 0]], dtype=np.float64)
+    f = np.array([10.0, -10.0, 0.0, 3.3, -7.0, 10.0, 1.0, 0.0])
+    with np.errstate(all="ignore"):
+        a = O.cartpole_step_f64ref(st, f, 0.02, 3, p, libm=True)
+        b = C.cartpole_step_f64ref(st, f, 0.02, 3, p)
+        assert np.array_equal(a, b, equal_nan=True)
+        r, d = C.cartpole_reward_terminal("swingup", st, p)
+        assert np.array_equal(d, O.cartpole_terminal("swingup", st, p))  # |x| == 5 and NaN are terminal
+        assert np.array_equal(r, O.cartpole_reward("swingup", st), equal_nan=True)
+        bal = O.cartpole_params("balancing")
+        r, d = C.cartpole_reward_terminal("balancing", st, bal)
+        assert np.array_equal(d, O.cartpole_terminal("balancing", st, bal)) and np.all(r == 1.0)
+        ip = O.InvertedPendulumParams()
+        s1, o1 = O.ip_step(st, np.clip(f, -3, 3), 0.02, 2, True, ip, libm=True)
+        s2, o2 = C.ip_step(st, np.clip(f, -3, 3), 0.02, 2, True, ip)
+        assert np.array_equal(s1, s2, equal_nan=True) and np.array_equal(o1, o2, equal_nan=True)
+    hp = O.HopperParams(terminate_when_unhealthy=False)
+    obs = np.ones((4, 12))
+    obs[1, 5] = np.nan
+    obs[2, 1] = 0.7       # healthy_z is a strict inequality (hopper.py:86-88)
+    obs[3, 7] = 100.0     # and so is the state range
+    r, d = C.hopper_reward_terminal(obs, obs, np.zeros((4, 3)), hp)
+    assert np.array_equal(d, O.hopper_terminal(obs, hp)) and d[:, 0].tolist() == [False, True, True, True]
+    assert np.array_equal(r, O.hopper_reward(obs, obs, np.zeros((4, 3)), hp))
