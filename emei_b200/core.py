@@ -69,6 +69,7 @@ class EmeiEnv(Freezable):
         self._stats = None
         self._seed = 0
         self._reset_count = 0
+        self._rollout_epoch = -1  # resets since the last explicit seed (0 = the seeded one): keys the rollout / noise streams
 
     # ------------------------------------------------------------------ device plumbing
     @property
@@ -226,13 +227,34 @@ class EmeiEnv(Freezable):
         rp.auto_reset = int(bool(auto_reset))
         rp.random_policy = int(actions is None)
         rp.env_offset = int(getattr(self, "env_offset", 0))
-        rp.seed_reset = (self._seed * 0x9E3779B97F4A7C15 + 0x5851F42D4C957F2D) & 0xFFFFFFFFFFFFFFFF
-        rp.seed_action = (self._seed * 0xD1B54A32D192ED03 + 0x14057B7EF767814F) & 0xFFFFFFFFFFFFFFFF
+        # reset() zeroes the episode / step counters of the streams, so the streams themselves must change with every
+        # un-seeded reset: `env.reset(); env.rollout(T)` in a loop (offline.collect_dataset) would otherwise replay the
+        # same random actions and in-kernel reset samples each cycle.  reset(seed=s) restarts at epoch 0 (reproducible).
+        epoch = max(self._rollout_epoch, 0)
+        rp.seed_reset = (self._seed * 0x9E3779B97F4A7C15 + 0x5851F42D4C957F2D + epoch * 0xA0761D6478BD642F) & 0xFFFFFFFFFFFFFFFF
+        rp.seed_action = (self._seed * 0xD1B54A32D192ED03 + 0x14057B7EF767814F + epoch * 0xE7037ED1A0B428DB) & 0xFFFFFFFFFFFFFFFF
         a = None
         if actions is not None:
+            # same dtype / range rules as step() (engine.normalise_action; base_control.py:62-66)
             a, _ = self._to_device(actions)
+            cont = len(self.action_space.shape) > 0
             if a.dtype == torch.bool:
                 a = a.view(torch.uint8)
+            if cont:
+                if a.dtype not in (torch.float32, torch.float64):
+                    a = a.to(torch.float32)
+            else:
+                if a.dtype.is_floating_point:
+                    raise AssertionError(f"actions of dtype {a.dtype} invalid: discrete action space needs integers")
+                if a.dtype not in (torch.uint8, torch.int32, torch.int64):
+                    a = a.to(torch.int64)
+            if getattr(self, "validate_actions", False):  # device-side range check: one sync, off by default
+                if cont:
+                    lo, hi = float(self.action_space.low.min()), float(self.action_space.high.max())
+                    ok = bool(((a >= lo) & (a <= hi)).all())
+                else:
+                    ok = bool(((a >= 0) & (a < self.action_space.n)).all())
+                assert ok, "teacher-forced actions outside the action space"
         stats = torch.zeros(6, dtype=torch.float64, device=self.device)
         out = eng.rollout(rp, a, bool(record), stats)
         out["stats"] = stats
@@ -270,6 +292,9 @@ class EmeiEnv(Freezable):
         if seed is not None:
             self._seed = int(seed) & 0xFFFFFFFFFFFFFFFF
             self._reset_count = 0
+            self._rollout_epoch = 0
+        else:
+            self._rollout_epoch += 1
 
     def _next_sample_seed(self):
         """A fresh Philox key per sampling call: (seed, call counter) so repeated resets differ but a

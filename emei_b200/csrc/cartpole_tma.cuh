@@ -343,13 +343,18 @@ inline void tma_ring_shape(int action_bytes, int64_t chunks_per_cta, int* n_slot
   *smem_bytes = static_cast<size_t>(s) * slot_bytes + 2 * s * sizeof(uint64_t) + (kTmaThreads / 32) * (sizeof(double) + sizeof(unsigned)) + 16;
 }
 
+// opt in to > 48 KB of dynamic shared memory: the attribute is PER DEVICE, so it is set once per (kernel
+// instantiation, device); a failure surfaces as the launch status of the call that needed it
 template <auto Kernel>
-inline void tma_allow_smem() {  // opt in to > 48 KB of dynamic shared memory, once per kernel instantiation
-  static const bool once = []() {
-    cudaFuncSetAttribute(Kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    return true;
-  }();
-  (void)once;
+inline cudaError_t tma_allow_smem() {
+  static bool done[kMaxDevices] = {};
+  const int d = current_device();
+  if (!done[d]) {
+    const cudaError_t e = cudaFuncSetAttribute(Kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return e;
+    done[d] = true;
+  }
+  return cudaSuccess;
 }
 
 template <typename... KArgs, typename... Args>
@@ -398,7 +403,8 @@ inline void launch_cartpole_f32_tma(int ak, cudaStream_t s, const float* state_i
   for (int64_t off = 0; off < n; off += kCartPoleMaxLaunch) {
     const int64_t m = n - off < kCartPoleMaxLaunch ? n - off : kCartPoleMaxLaunch;
     const int64_t chunks = (m + kChunk - 1) / kChunk;
-    const int grid = static_cast<int>(chunks < kNumSMs ? chunks : kNumSMs);
+    const int n_sm = sm_count();
+    const int grid = static_cast<int>(chunks < n_sm ? chunks : n_sm);
     int n_slots;
     size_t smem;
     tma_ring_shape(action_bytes, (chunks + grid - 1) / grid, &n_slots, &smem);
@@ -411,13 +417,13 @@ inline void launch_cartpole_f32_tma(int ak, cudaStream_t s, const float* state_i
 #define EMEI_AK(A)                                                                                                       \
   case A:                                                                                                                \
     if (obs4 != nullptr) {                                                                                               \
-      tma_allow_smem<cartpole_step_f32_tma_kernel<IP, A, FR, true>>();                                                     \
-      launch_pdl_smem(cartpole_step_f32_tma_kernel<IP, A, FR, true>, grid, kTmaThreads, smem, s, in4, out4, obs4, act,   \
-                      reward + off, done + off, stats, static_cast<uint32_t>(m), n_slots, act_tma, k);                   \
+      if (tma_allow_smem<cartpole_step_f32_tma_kernel<IP, A, FR, true>>() == cudaSuccess)                                  \
+        launch_pdl_smem(cartpole_step_f32_tma_kernel<IP, A, FR, true>, grid, kTmaThreads, smem, s, in4, out4, obs4, act, \
+                        reward + off, done + off, stats, static_cast<uint32_t>(m), n_slots, act_tma, k);                 \
     } else {                                                                                                             \
-      tma_allow_smem<cartpole_step_f32_tma_kernel<IP, A, FR, false>>();                                                    \
-      launch_pdl_smem(cartpole_step_f32_tma_kernel<IP, A, FR, false>, grid, kTmaThreads, smem, s, in4, out4, obs4, act,  \
-                      reward + off, done + off, stats, static_cast<uint32_t>(m), n_slots, act_tma, k);                   \
+      if (tma_allow_smem<cartpole_step_f32_tma_kernel<IP, A, FR, false>>() == cudaSuccess)                                 \
+        launch_pdl_smem(cartpole_step_f32_tma_kernel<IP, A, FR, false>, grid, kTmaThreads, smem, s, in4, out4, obs4, act, \
+                        reward + off, done + off, stats, static_cast<uint32_t>(m), n_slots, act_tma, k);                 \
     }                                                                                                                    \
     break;
       EMEI_AK(EMEI_ACTION_DISCRETE_U8)

@@ -8,7 +8,26 @@
 namespace emei {
 
 constexpr int kBlock = 256;   // threads per CTA for the streaming kernels
-constexpr int kNumSMs = 148;  // B200
+constexpr int kNumSMs = 148;  // B200 (upper bound used for workspace sizes; launches query the device, sm_count())
+constexpr int kMaxDevices = 64;
+
+inline int current_device() {
+  int d = 0;
+  if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= kMaxDevices) d = 0;
+  return d;
+}
+
+// SM count of the CURRENT device (a process may drive envs on several GPUs); cached per device, immutable after first use
+inline int sm_count() {
+  static int cache[kMaxDevices] = {};
+  const int d = current_device();
+  int v = cache[d];
+  if (v <= 0) {
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, d) != cudaSuccess || v <= 0) v = kNumSMs;
+    cache[d] = v;  // benign race: every thread writes the same value
+  }
+  return v;
+}
 
 #define EMEI_CHECK_PTR(p) \
   if ((p) == nullptr) return EMEI_ERR_NULL_POINTER
@@ -29,7 +48,7 @@ inline int grid_for(int64_t n, int per_block) {
 // (the kernels grid-stride over the rest, so every SM carries the same number of units +-1)
 inline int persistent_grid(int64_t n, int per_block, int ctas_per_sm) {
   const int64_t want = (n + per_block - 1) / per_block;
-  const int64_t cap = static_cast<int64_t>(kNumSMs) * ctas_per_sm;
+  const int64_t cap = static_cast<int64_t>(sm_count()) * ctas_per_sm;
   return static_cast<int>(want < 1 ? 1 : (want > cap ? cap : want));
 }
 
@@ -38,12 +57,14 @@ inline int persistent_grid(int64_t n, int per_block, int ctas_per_sm) {
 // occupancy query result is cached per kernel instantiation (immutable after first use).
 template <typename... KArgs>
 inline int resident_grid(void (*kernel)(KArgs...), int64_t n) {
-  static const int per_sm = [kernel]() {
-    int nb = 0;
+  static int per_sm[kMaxDevices] = {};  // per kernel instantiation AND per device
+  const int d = current_device();
+  int nb = per_sm[d];
+  if (nb < 1) {
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, kBlock, 0) != cudaSuccess || nb < 1) nb = 4;
-    return nb;
-  }();
-  return persistent_grid(n, kBlock, per_sm);
+    per_sm[d] = nb;
+  }
+  return persistent_grid(n, kBlock, nb);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -467,85 +467,93 @@ struct FamilyDim {
                                                                                                                 : 4;
 };
 
+// reward and not-done flag of ONE transition row (o = obs row, p0 = pre_obs[:, 0] for Hopper / HalfCheetah,
+// ctrl_cost = ctrl_cost_weight * sum over the WHOLE batch of action^2)
+template <typename R, int FAMILY, int D>
+__device__ __forceinline__ void score_row(const R (&o)[D], R p0, R ctrl_cost, const ScoringConsts<R>& k, R& rew, bool& notdone) {
+  if constexpr (FAMILY == EMEI_CARTPOLE_BALANCING) {  // cartpole.py:124-129
+    rew = R(1);
+    notdone = (abs_r(o[2]) < k.th_thr) && (abs_r(o[0]) < k.x_thr);
+  } else if constexpr (FAMILY == EMEI_CARTPOLE_SWINGUP) {  // cartpole.py:145-151
+    rew = (cos_r(o[2]) + R(1)) / R(2);
+    notdone = abs_r(o[0]) < k.x_thr;
+  } else if constexpr (FAMILY >= EMEI_IP_REBOUND_BALANCING && FAMILY <= EMEI_IP_BOUNDARY_SWINGUP) {
+    const bool finite = row_finite<R, D>(o);
+    const R cy = cos_r(o[1]);
+    const bool in_rail = (k.x_left < o[0]) && (o[0] < k.x_right);
+    if constexpr (FAMILY == EMEI_IP_REBOUND_BALANCING) {  // inverted_pendulum.py:73-79
+      rew = R(1);
+      notdone = (cy >= R(0.9)) && finite;
+    } else if constexpr (FAMILY == EMEI_IP_BOUNDARY_BALANCING) {  // :103-111
+      rew = R(1);
+      notdone = (cy >= R(0)) && in_rail && finite;
+    } else if constexpr (FAMILY == EMEI_IP_REBOUND_SWINGUP) {  // :139-146
+      rew = (R(1) - cy) / R(2);
+      notdone = finite;
+    } else {  // :174-183
+      rew = (R(1) - cy) / R(2);
+      notdone = in_rail && finite;
+    }
+  } else if constexpr (FAMILY >= EMEI_I2P_REBOUND_BALANCING && FAMILY <= EMEI_I2P_BOUNDARY_SWINGUP) {
+    const bool finite = row_finite<R, D>(o);
+    const R y = cos_r(o[1]) + cos_r(o[1] + o[2]);  // inverted_double_pendulum.py:88
+    const bool in_rail = (k.x_left < o[0]) && (o[0] < k.x_right);
+    if constexpr (FAMILY == EMEI_I2P_REBOUND_BALANCING) {  // :84-90
+      rew = R(1);
+      notdone = (y >= R(1.5)) && finite;
+    } else if constexpr (FAMILY == EMEI_I2P_BOUNDARY_BALANCING) {  // :114-122
+      rew = R(1);
+      notdone = (y >= R(0)) && in_rail && finite;
+    } else if constexpr (FAMILY == EMEI_I2P_REBOUND_SWINGUP) {  // :150-157
+      rew = (R(2) - y) / R(4);
+      notdone = finite;
+    } else {  // :185-196
+      const R vel_penalty = R(5e-3) * (o[4] * o[4]) + R(1e-4) * (o[5] * o[5]);
+      rew = (R(2) - y) / R(4) - vel_penalty;
+      notdone = in_rail && finite;
+    }
+  } else if constexpr (FAMILY == EMEI_HOPPER) {
+    // hopper.py:79-106.  healthy_angle is computed and discarded by the reference (np.logical_and's
+    // third positional argument is out=, hopper.py:91) -- replicated: only state and z count.
+    bool healthy = (k.hz_lo < o[1]) && (o[1] < k.hz_hi);
+#pragma unroll
+    for (int j = 2; j < D; ++j) healthy = healthy && (k.hs_lo < o[j]) && (o[j] < k.hs_hi);
+    const bool alive = healthy || (k.terminate_when_unhealthy != 0);
+    const R x_velocity = (o[0] - p0) / k.dt;
+    const R control_cost = ctrl_cost;
+    const R healthy_reward = alive ? k.healthy_reward : R(0) * k.healthy_reward;
+    rew = healthy_reward + k.fwd_w * x_velocity - control_cost;
+    notdone = alive;
+  } else if constexpr (FAMILY == EMEI_HALFCHEETAH) {  // half_cheetah.py:59-67
+    const R control_cost = ctrl_cost;
+    rew = k.fwd_w * (o[0] - p0) / k.dt - control_cost;
+    notdone = row_finite<R, D>(o);
+  } else {  // EMEI_CHARGED_BALL charged_ball.py:110-111,158-160
+    rew = R(1) - sqrt_r(o[0] * o[0] + o[1] * o[1]) / k.radius;
+    notdone = true;
+  }
+}
+
 template <typename R, int FAMILY>
 __global__ void __launch_bounds__(kBlock)
     reward_terminal_kernel(const R* __restrict__ obs, const R* __restrict__ pre_obs, R* __restrict__ reward,
                            uint8_t* __restrict__ done, double* stats, const double* __restrict__ sumsq, int64_t n,
                            const ScoringConsts<R> k) {
   constexpr int D = FamilyDim<R, FAMILY>::value;
+  constexpr bool kNeedsPre = FAMILY == EMEI_HOPPER || FAMILY == EMEI_HALFCHEETAH;
   const int64_t stride = static_cast<int64_t>(gridDim.x) * kBlock;
   double r_acc = 0.0;
   unsigned d_cnt = 0;
   [[maybe_unused]] R ctrl_cost = R(0);
-  if constexpr (FAMILY == EMEI_HOPPER || FAMILY == EMEI_HALFCHEETAH) ctrl_cost = k.ctrl_w * static_cast<R>(*sumsq);
+  if constexpr (kNeedsPre) ctrl_cost = k.ctrl_w * static_cast<R>(*sumsq);
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * kBlock + threadIdx.x; i < n; i += stride) {
     alignas(16) R o[D];
     load_row<R, D>(obs, i, o);
+    R p0 = R(0);
+    if constexpr (kNeedsPre) p0 = __ldg(pre_obs + i * D);
     R rew;
     bool notdone;
-    if constexpr (FAMILY == EMEI_CARTPOLE_BALANCING) {  // cartpole.py:124-129
-      rew = R(1);
-      notdone = (abs_r(o[2]) < k.th_thr) && (abs_r(o[0]) < k.x_thr);
-    } else if constexpr (FAMILY == EMEI_CARTPOLE_SWINGUP) {  // cartpole.py:145-151
-      rew = (cos_r(o[2]) + R(1)) / R(2);
-      notdone = abs_r(o[0]) < k.x_thr;
-    } else if constexpr (FAMILY >= EMEI_IP_REBOUND_BALANCING && FAMILY <= EMEI_IP_BOUNDARY_SWINGUP) {
-      const bool finite = row_finite<R, D>(o);
-      const R cy = cos_r(o[1]);
-      const bool in_rail = (k.x_left < o[0]) && (o[0] < k.x_right);
-      if constexpr (FAMILY == EMEI_IP_REBOUND_BALANCING) {  // inverted_pendulum.py:73-79
-        rew = R(1);
-        notdone = (cy >= R(0.9)) && finite;
-      } else if constexpr (FAMILY == EMEI_IP_BOUNDARY_BALANCING) {  // :103-111
-        rew = R(1);
-        notdone = (cy >= R(0)) && in_rail && finite;
-      } else if constexpr (FAMILY == EMEI_IP_REBOUND_SWINGUP) {  // :139-146
-        rew = (R(1) - cy) / R(2);
-        notdone = finite;
-      } else {  // :174-183
-        rew = (R(1) - cy) / R(2);
-        notdone = in_rail && finite;
-      }
-    } else if constexpr (FAMILY >= EMEI_I2P_REBOUND_BALANCING && FAMILY <= EMEI_I2P_BOUNDARY_SWINGUP) {
-      const bool finite = row_finite<R, D>(o);
-      const R y = cos_r(o[1]) + cos_r(o[1] + o[2]);  // inverted_double_pendulum.py:88
-      const bool in_rail = (k.x_left < o[0]) && (o[0] < k.x_right);
-      if constexpr (FAMILY == EMEI_I2P_REBOUND_BALANCING) {  // :84-90
-        rew = R(1);
-        notdone = (y >= R(1.5)) && finite;
-      } else if constexpr (FAMILY == EMEI_I2P_BOUNDARY_BALANCING) {  // :114-122
-        rew = R(1);
-        notdone = (y >= R(0)) && in_rail && finite;
-      } else if constexpr (FAMILY == EMEI_I2P_REBOUND_SWINGUP) {  // :150-157
-        rew = (R(2) - y) / R(4);
-        notdone = finite;
-      } else {  // :185-196
-        const R vel_penalty = R(5e-3) * (o[4] * o[4]) + R(1e-4) * (o[5] * o[5]);
-        rew = (R(2) - y) / R(4) - vel_penalty;
-        notdone = in_rail && finite;
-      }
-    } else if constexpr (FAMILY == EMEI_HOPPER) {
-      // hopper.py:79-106.  healthy_angle is computed and discarded by the reference (np.logical_and's
-      // third positional argument is out=, hopper.py:91) -- replicated: only state and z count.
-      bool healthy = (k.hz_lo < o[1]) && (o[1] < k.hz_hi);
-#pragma unroll
-      for (int j = 2; j < D; ++j) healthy = healthy && (k.hs_lo < o[j]) && (o[j] < k.hs_hi);
-      const bool alive = healthy || (k.terminate_when_unhealthy != 0);
-      const R p0 = __ldg(pre_obs + i * D);
-      const R x_velocity = (o[0] - p0) / k.dt;
-      const R control_cost = ctrl_cost;
-      const R healthy_reward = alive ? k.healthy_reward : R(0) * k.healthy_reward;
-      rew = healthy_reward + k.fwd_w * x_velocity - control_cost;
-      notdone = alive;
-    } else if constexpr (FAMILY == EMEI_HALFCHEETAH) {  // half_cheetah.py:59-67
-      const R p0 = __ldg(pre_obs + i * D);
-      const R control_cost = ctrl_cost;
-      rew = k.fwd_w * (o[0] - p0) / k.dt - control_cost;
-      notdone = row_finite<R, D>(o);
-    } else {  // EMEI_CHARGED_BALL charged_ball.py:110-111,158-160
-      rew = R(1) - sqrt_r(o[0] * o[0] + o[1] * o[1]) / k.radius;
-      notdone = true;
-    }
+    score_row<R, FAMILY, D>(o, p0, ctrl_cost, k, rew, notdone);
     reward[i] = rew;
     done[i] = notdone ? 0 : 1;
     r_acc += static_cast<double>(rew);
@@ -554,9 +562,85 @@ __global__ void __launch_bounds__(kBlock)
   block_stats_accumulate_counts(stats, r_acc, d_cnt);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Trajectory ("sequence") scoring for Hopper / HalfCheetah: rows whose pre_obs IS the observation one time step
+// earlier.  An imagined rollout is a tensor obs_seq[T+1, k, D]; its transitions are obs = obs_seq[1:], pre_obs =
+// obs_seq[:-1], i.e. pre_obs + k*D == obs: transition row i = t*k + j reads pre_obs[i] == obs[i - k].  Reading
+// `pre_obs[:, 0]` as a separate strided column costs the WHOLE pre_obs array in DRAM traffic (a 4-byte column of
+// 48 / 72-byte rows touches every 64-byte DRAM atom: ncu measured 1.46x / 1.42x the algorithmic bytes, profiles/
+// r01_ncu_full_c3_*.txt), so here a thread owns env column j and walks t, carrying obs[t-1][0] in a register:
+// every obs row is read exactly once (65 / 101 B per transition instead of 113 / 173 B of DRAM traffic).
+// A thread handles a segment of `seg_len` consecutive time steps (grid.y = segments), reading the one strided
+// pre_obs value of its first row; the next row's loads are issued before the current row is scored.
+// ---------------------------------------------------------------------------------------------
+template <typename R, int FAMILY>
+__global__ void __launch_bounds__(kBlock)
+    reward_terminal_seq_kernel(const R* __restrict__ obs, const R* __restrict__ pre_obs, R* __restrict__ reward,
+                               uint8_t* __restrict__ done, double* stats, const double* __restrict__ sumsq, int64_t n,
+                               int64_t k_envs, int64_t seg_len, const ScoringConsts<R> k) {
+  constexpr int D = FamilyDim<R, FAMILY>::value;
+  const int64_t j = static_cast<int64_t>(blockIdx.x) * kBlock + threadIdx.x;  // env column
+  const int64_t t0 = static_cast<int64_t>(blockIdx.y) * seg_len;
+  double r_acc = 0.0;
+  unsigned d_cnt = 0;
+  const R ctrl_cost = k.ctrl_w * static_cast<R>(*sumsq);
+  int64_t i = t0 * k_envs + j;  // first transition row of this thread
+  if (j < k_envs && i < n) {
+    alignas(16) R o[D], nx[D];
+    R p0 = __ldg(pre_obs + i * D);
+    load_row<R, D>(obs, i, o);
+    for (int64_t s = 0; s < seg_len && i < n; ++s) {
+      const int64_t i_next = i + k_envs;
+      const bool more = s + 1 < seg_len && i_next < n;
+      if (more) load_row<R, D>(obs, i_next, nx);
+      R rew;
+      bool notdone;
+      score_row<R, FAMILY, D>(o, p0, ctrl_cost, k, rew, notdone);
+      reward[i] = rew;
+      done[i] = notdone ? 0 : 1;
+      r_acc += static_cast<double>(rew);
+      d_cnt += notdone ? 0u : 1u;
+      p0 = o[0];
+#pragma unroll
+      for (int c = 0; c < D; ++c) o[c] = nx[c];
+      i = i_next;
+    }
+  }
+  block_stats_accumulate_counts(stats, r_acc, d_cnt);
+}
+
+// rows are scored by the sequence kernel when pre_obs + k*D == obs for a column count k that keeps the walk
+// coalesced; the address identity alone makes pre_obs[i] and obs[i - k] the same memory, whatever the allocation
+constexpr int64_t kSeqMinEnvs = 256;
+template <typename R>
+inline int64_t scoring_alias_columns(const R* obs, const R* pre_obs, int dim, int64_t n) {
+  if (pre_obs == nullptr || obs <= pre_obs) return 0;
+  const int64_t diff = obs - pre_obs;  // elements
+  if (diff % dim != 0) return 0;
+  const int64_t k = diff / dim;
+  return (k >= kSeqMinEnvs && k < n) ? k : 0;
+}
+
 template <typename R, int FAMILY>
 void launch_reward_terminal(const R* obs, const R* pre_obs, R* reward, uint8_t* done, double* stats, const double* sumsq,
                             int64_t n, const ScoringConsts<R>& k, cudaStream_t s) {
+  if constexpr (FAMILY == EMEI_HOPPER || FAMILY == EMEI_HALFCHEETAH) {
+    const int64_t cols = scoring_alias_columns<R>(obs, pre_obs, FamilyDim<R, FAMILY>::value, n);
+    if (cols > 0) {
+      const int64_t T = (n + cols - 1) / cols;
+      // enough segments for ~2^20 threads in flight, at least 8 time steps each (one strided pre_obs read per segment)
+      int64_t segs = ((int64_t{1} << 20) + cols - 1) / cols;
+      const int64_t max_segs = (T + 7) / 8;
+      if (segs > max_segs) segs = max_segs;
+      if (segs < 1) segs = 1;
+      if (segs > 65535) segs = 65535;
+      const int64_t seg_len = (T + segs - 1) / segs;
+      segs = (T + seg_len - 1) / seg_len;
+      const dim3 grid(static_cast<unsigned>(grid_for(cols, kBlock)), static_cast<unsigned>(segs), 1);
+      reward_terminal_seq_kernel<R, FAMILY><<<grid, kBlock, 0, s>>>(obs, pre_obs, reward, done, stats, sumsq, n, cols, seg_len, k);
+      return;
+    }
+  }
   // without statistics: one row per thread over a full grid (measured 9 % faster than the persistent
   // loop for these load-dominated rows); with statistics: one resident wave, partials in registers
   const int grid = stats == nullptr ? grid_for(n, kBlock) : resident_grid(reward_terminal_kernel<R, FAMILY>, n);
@@ -605,6 +689,21 @@ int reward_terminal(const R* obs, const R* pre_obs, R* reward, uint8_t* done, do
   return launch_status();
 }
 
+// trajectory form: obs_seq [horizon + 1, n_envs, D]; transition (t, j) has obs = obs_seq[t + 1, j], pre_obs = obs_seq[t, j]
+template <typename R>
+int reward_terminal_seq(const R* obs_seq, R* reward, uint8_t* done, double* stats, const double* sumsq, int64_t n_envs,
+                        int64_t horizon, const emei_scoring_params* p, emei_stream_t stream) {
+  if (n_envs < 0 || horizon < 0) return EMEI_ERR_BAD_SIZE;
+  EMEI_CHECK_PTR(p);
+  if (p->family < 0 || p->family >= EMEI_NUM_FAMILIES) return EMEI_ERR_BAD_VARIANT;
+  if (n_envs == 0 || horizon == 0) return EMEI_OK;
+  EMEI_CHECK_PTR(obs_seq);
+  const int dim = emei_family_obs_dim(p->family);
+  // the rows of t >= 1 must keep the 16-byte alignment of the row loader
+  if ((static_cast<uint64_t>(n_envs) * dim * sizeof(R)) % 16 != 0) return EMEI_ERR_MISALIGNED;
+  return reward_terminal<R>(obs_seq + n_envs * dim, obs_seq, reward, done, stats, sumsq, n_envs * horizon, p, stream);
+}
+
 // =============================================================================================
 // sum of squares (batch-wide control cost, hopper.py:98 / half_cheetah.py:61)
 // =============================================================================================
@@ -621,7 +720,21 @@ __global__ void __launch_bounds__(kBlock) sumsq_kernel(const R* __restrict__ x, 
   const int64_t nvec = n / V;
   double acc = 0.0;
   const int64_t stride = static_cast<int64_t>(gridDim.x) * kBlock;
-  for (int64_t j = static_cast<int64_t>(blockIdx.x) * kBlock + threadIdx.x; j < nvec; j += stride) {
+  // four independent 128-bit loads in flight per thread (a single dependent load per iteration left this pass at
+  // 5 TB/s); the summation order per thread is fixed, so the result stays bit-reproducible
+  int64_t j = static_cast<int64_t>(blockIdx.x) * kBlock + threadIdx.x;
+  for (; j + 3 * stride < nvec; j += 4 * stride) {
+    uint4 q[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) q[u] = __ldg(reinterpret_cast<const uint4*>(x) + j + u * stride);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const R* v = reinterpret_cast<const R*>(&q[u]);
+#pragma unroll
+      for (int e = 0; e < V; ++e) acc += static_cast<double>(v[e]) * static_cast<double>(v[e]);
+    }
+  }
+  for (; j < nvec; j += stride) {
     const uint4 q = __ldg(reinterpret_cast<const uint4*>(x) + j);
     const R* v = reinterpret_cast<const R*>(&q);
 #pragma unroll

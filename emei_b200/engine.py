@@ -56,7 +56,9 @@ def normalise_action(env, action, continuous: bool) -> torch.Tensor:
 
 
 class StepOutputs:
-    """Ping-pong output buffers: what step t returns stays valid until step t+2 overwrites it."""
+    """Ping-pong reward / done buffers of the zero-copy mode (``copy_outputs=False``): what step t returns stays valid
+    until step t+2 overwrites it (the charged ball's observation is the live ``free`` array: valid until step t+1).
+    The default ``copy_outputs=True`` returns fresh tensors instead, like the reference's ``state.copy()``."""
 
     def __init__(self, n, dtype, device):
         self.reward = [torch.empty((n, 1), dtype=dtype, device=device) for _ in range(2)]
@@ -416,12 +418,46 @@ class ChargedBallEngine(RolloutMixin):
         self.has_state = True
 
 
+def _aligned16(t: torch.Tensor) -> torch.Tensor:
+    """The row loaders use 128-bit accesses: a contiguous view that starts at an odd offset (``obs[k:]`` of 12-byte
+    action rows or 72-byte observation rows) is copied to a fresh, aligned allocation (the reference accepts any slice)."""
+    return t if t.data_ptr() % 16 == 0 else t.clone()
+
+
+def _sumsq(env, a: torch.Tensor, group):
+    """batch-wide sum of squared actions (hopper.py:98 / half_cheetah.py:61), all-reduced when the batch is sharded."""
+    sumsq = torch.empty(1, dtype=torch.float64, device=env.device)
+    ws = getattr(env, "_sumsq_ws", None)
+    if ws is None:  # zero-filled once; the kernel leaves its ticket counter at zero
+        ws = env._sumsq_ws = torch.zeros(_lib.SUMSQ_WORKSPACE_BYTES // 8, dtype=torch.float64, device=env.device)
+    env._call("emei_sumsq", a.data_ptr(), a.numel(), sumsq.data_ptr(), ws.data_ptr(), env._stream())
+    if getattr(env, "ctrl_cost_scope", "global") == "global":
+        from .dist import all_reduce_sum_
+
+        all_reduce_sum_(sumsq, group)
+    return sumsq
+
+
+def _score_cache_key(env, params, tensors, group):
+    """Identity of one scoring call: same tensors (address, shape, torch version counter), same parameters, same
+    stream, and NO emei kernel launched since the cached pass (our kernels write through raw pointers and do not
+    bump torch's version counters)."""
+    ident = tuple((t.data_ptr(), tuple(t.shape), t._version, t.dtype) if t is not None else None for t in tensors)
+    return (ident, bytes(params), env._stream(), id(group))
+
+
 def score(env, params: _lib.ScoringParams, obs, pre_obs=None, action=None, want="both", group=None):
     """Fused get_batch_reward + get_batch_terminal through emei_reward_terminal_* for any batch size.
 
     Hopper/HalfCheetah: pass 1 = emei_sumsq_* over the action batch (the reference sums the control
     cost over the WHOLE batch, hopper.py:98 / half_cheetah.py:61), optional all-reduce of that one
-    double across ranks when the batch is sharded, pass 2 = the fused row kernel.
+    double across ranks when the batch is sharded, pass 2 = the fused row kernel.  When ``pre_obs`` and
+    ``obs`` are the two shifted views of one trajectory tensor (``seq[:-1]`` / ``seq[1:]``) the C side
+    walks the trajectory and reads every observation row once (include/emei_b200.h).
+
+    The reference's API has two calls (get_batch_reward, get_batch_terminal: mujoco_env.py:163-169 callers);
+    a caller that makes them back to back on the SAME device tensors gets the second answer from the first
+    call's fused pass (one row pass instead of two).
     Returns (reward [B,1] or None, done bool[B,1] or None, came_from_numpy)."""
     family = params.family
     o, was_np = env._to_device(obs, env.dtype)
@@ -429,27 +465,38 @@ def score(env, params: _lib.ScoringParams, obs, pre_obs=None, action=None, want=
         raise ValueError(f"obs must be [B,{_lib.lib.emei_family_obs_dim(family)}], got {tuple(o.shape)}")
     b = o.shape[0]
     needs_pre = family in (_lib.HOPPER, _lib.HALFCHEETAH)
-    p = sumsq = None
-    if needs_pre and want != "terminal":
+    p = a = None
+    if needs_pre and (want != "terminal" or (pre_obs is not None and action is not None)):
         if pre_obs is None or action is None:
             raise TypeError("get_batch_reward of this env needs obs, pre_obs and action")
         p, _ = env._to_device(pre_obs, env.dtype)
         a, _ = env._to_device(action, env.dtype)
         if tuple(p.shape) != tuple(o.shape) or a.shape[0] != b:
             raise ValueError("obs / pre_obs / action batch shapes disagree")
-        sumsq = torch.empty(1, dtype=torch.float64, device=env.device)
-        ws = getattr(env, "_sumsq_ws", None)
-        if ws is None:  # zero-filled once; the kernel leaves its ticket counter at zero
-            ws = env._sumsq_ws = torch.zeros(_lib.SUMSQ_WORKSPACE_BYTES // 8, dtype=torch.float64, device=env.device)
-        env._call("emei_sumsq", a.data_ptr(), a.numel(), sumsq.data_ptr(), ws.data_ptr(), env._stream())
-        if getattr(env, "ctrl_cost_scope", "global") == "global":
-            from .dist import all_reduce_sum_
-
-            all_reduce_sum_(sumsq, group)
+    # ---- the other half of a reward / terminal pair asked for on the same tensors: reuse the fused pass
+    key = key_obs = None
+    if not was_np:
+        key_obs = _score_cache_key(env, params, (o,), group)
+        hit = getattr(env, "_score_cache", None)
+        if hit is not None and hit[2] == _lib.launch_count:
+            if not needs_pre or p is not None:
+                key = _score_cache_key(env, params, (o, p, a), group)
+                if hit[0] == key:
+                    return hit[3], hit[4], was_np
+            elif hit[1] == key_obs:  # terminal asked for with obs alone: the flags depend on obs only
+                return None, hit[4], was_np
+        if key is None and (not needs_pre or p is not None):
+            key = _score_cache_key(env, params, (o, p, a), group)
+    sumsq = None
+    if needs_pre and p is not None:
+        sumsq = _sumsq(env, _aligned16(a), group)
+        if p.data_ptr() % 16 != 0 or o.data_ptr() % 16 != 0:  # keep the seq[:-1] / seq[1:] address relation when both are aligned
+            p = _aligned16(p)
     elif needs_pre:
         # terminal only: reward inputs are not needed; feed harmless placeholders
         p = o
         sumsq = torch.zeros(1, dtype=torch.float64, device=env.device)
+    o = _aligned16(o)
     reward = torch.empty((b, 1), dtype=env.dtype, device=env.device)
     done = torch.empty((b, 1), dtype=torch.uint8, device=env.device)
     env._call(
@@ -457,6 +504,42 @@ def score(env, params: _lib.ScoringParams, obs, pre_obs=None, action=None, want=
         o.data_ptr(), p.data_ptr() if p is not None else None, reward.data_ptr(), done.data_ptr(),
         env.stats.data_ptr() if getattr(env, "accumulate_scoring_stats", False) else None,
         sumsq.data_ptr() if sumsq is not None else None, b, ctypes.byref(params), env._stream(),
+    )
+    done = done.view(torch.bool)
+    if key is not None and not getattr(env, "accumulate_scoring_stats", False):
+        env._score_cache = (key, key_obs, _lib.launch_count, reward, done)
+    return reward, done, was_np
+
+
+def score_seq(env, params: _lib.ScoringParams, obs_seq, action=None, group=None):
+    """Trajectory scoring through emei_reward_terminal_seq_*: ``obs_seq`` [T+1, n, D] (an imagined rollout),
+    ``action`` [T, n, A] -> reward [T, n, 1], done bool [T, n, 1].  Equal to ``score`` on
+    ``obs = obs_seq[1:], pre_obs = obs_seq[:-1]`` flattened; every observation row is read once."""
+    family = params.family
+    s, was_np = env._to_device(obs_seq, env.dtype)
+    d = _lib.lib.emei_family_obs_dim(family)
+    if s.dim() != 3 or s.shape[2] != d or s.shape[0] < 1:
+        raise ValueError(f"obs_seq must be [T+1, n, {d}], got {tuple(s.shape)}")
+    T, n = s.shape[0] - 1, s.shape[1]
+    needs_pre = family in (_lib.HOPPER, _lib.HALFCHEETAH)
+    sumsq = None
+    if needs_pre:
+        if action is None:
+            raise TypeError("get_batch_reward of this env needs the actions")
+        a, _ = env._to_device(action, env.dtype)
+        if a.shape[0] != T or a.shape[1] != n:
+            raise ValueError(f"action must be [T={T}, n={n}, A], got {tuple(a.shape)}")
+        sumsq = _sumsq(env, _aligned16(a), group)
+    s = _aligned16(s)
+    reward = torch.empty((T, n, 1), dtype=env.dtype, device=env.device)
+    done = torch.empty((T, n, 1), dtype=torch.uint8, device=env.device)
+    if (n * d * s.element_size()) % 16 != 0:  # rows of t >= 1 would lose the loader's alignment: score the flat views
+        r, dn, _ = score(env, params, s[1:].reshape(T * n, d), s[:-1].reshape(T * n, d).clone(), a if needs_pre else None, group=group)
+        return r.reshape(T, n, 1), dn.reshape(T, n, 1), was_np
+    env._call(
+        "emei_reward_terminal_seq", s.data_ptr(), reward.data_ptr(), done.data_ptr(),
+        env.stats.data_ptr() if getattr(env, "accumulate_scoring_stats", False) else None,
+        sumsq.data_ptr() if sumsq is not None else None, n, T, ctypes.byref(params), env._stream(),
     )
     return reward, done.view(torch.bool), was_np
 

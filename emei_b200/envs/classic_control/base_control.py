@@ -35,7 +35,7 @@ class BaseControlEnv(EmeiEnv):
         dtype=torch.float32,
         env_offset: int = 0,
         validate_actions: bool = False,
-        copy_outputs: bool = False,
+        copy_outputs: bool = True,
     ):
         if render_mode is not None:
             raise NotImplementedError("rendering is outside the emei_b200 hot path")
@@ -45,7 +45,11 @@ class BaseControlEnv(EmeiEnv):
         self.render_mode = render_mode
         self.env_offset = int(env_offset)  # global id of env 0 (sharding: keys the Philox streams)
         self.validate_actions = bool(validate_actions)
-        self.copy_outputs = bool(copy_outputs)  # True: step() returns freshly allocated tensors
+        # True (default, the reference's contract: base_control.py:47,69,76 return state.copy()): step() returns freshly
+        # allocated tensors the caller owns.  False (zero-copy opt-in): step() returns views of the engine's live
+        # ping-pong buffers -- valid until the NEXT step() (charged ball: obs is updated in place by it; cart-pole /
+        # pendulums: overwritten two steps later), and writing into them corrupts the env state.
+        self.copy_outputs = bool(copy_outputs)
         EmeiEnv.__init__(
             self,
             env_params=dict(freq_rate=freq_rate, real_time_scale=real_time_scale, integrator=integrator),

@@ -26,7 +26,7 @@ import torch
 
 from ... import _lib, spaces
 from ...core import EmeiEnv
-from ...engine import score
+from ...engine import score, score_seq
 
 
 class EmeiMujocoEnv(EmeiEnv):
@@ -50,7 +50,7 @@ class EmeiMujocoEnv(EmeiEnv):
         dtype=torch.float32,
         env_offset: int = 0,
         validate_actions: bool = False,
-        copy_outputs: bool = False,
+        copy_outputs: bool = True,
     ):
         if render_mode is not None:
             raise NotImplementedError("rendering is outside the emei_b200 hot path")
@@ -113,7 +113,7 @@ class EmeiMujocoEnv(EmeiEnv):
         z = _lib.NoiseParams()
         for j, v in enumerate(np.concatenate([sp, sv])):
             z.sigma[j] = float(v)
-        z.seed = (self._seed * 0xA24BAED4963EE407 + 0x9FB21C651E98DF25) & 0xFFFFFFFFFFFFFFFF
+        z.seed = (self._seed * 0xA24BAED4963EE407 + 0x9FB21C651E98DF25 + max(self._rollout_epoch, 0) * 0x8EBC6AF09C88C6E3) & 0xFFFFFFFFFFFFFFFF
         z.env_offset = self.env_offset
         z.step = self._noise_step
         self._noise_step += 1
@@ -170,6 +170,14 @@ class EmeiMujocoEnv(EmeiEnv):
     def get_batch_reward_terminal(self, obs, pre_obs=None, action=None):
         """Additive: both outputs from ONE fused row pass (what an MBRL scorer wants)."""
         r, d, was_np = score(self, self._scoring_params(), obs, pre_obs, action, want="both")
+        return self._ret(r, was_np), self._ret(d, was_np)
+
+    def get_batch_reward_terminal_seq(self, obs_seq, action=None):
+        """Additive: score a whole imagined rollout ``obs_seq`` [T+1, n, D] with ``action`` [T, n, A] ->
+        (reward [T, n, 1], terminal bool [T, n, 1]).  Same numbers as ``get_batch_reward`` / ``get_batch_terminal``
+        on ``obs = obs_seq[1:]``, ``pre_obs = obs_seq[:-1]`` (hopper.py:95-106, half_cheetah.py:59-67), with every
+        observation row read once (emei_reward_terminal_seq_*)."""
+        r, d, was_np = score_seq(self, self._scoring_params(), obs_seq, action)
         return self._ret(r, was_np), self._ret(d, was_np)
 
     # ---- dynamics: only where the reference has a closed form -------------------------------------

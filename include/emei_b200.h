@@ -255,6 +255,20 @@ int emei_reward_terminal_f32(const float* obs, const float* pre_obs, float* rewa
 int emei_reward_terminal_f64(const double* obs, const double* pre_obs, double* reward, uint8_t* done, double* stats,
                              const double* sumsq, int64_t n, const emei_scoring_params* p, emei_stream_t stream);
 
+/* Trajectory form of the same scoring (the layout an MBRL scorer holds its imagined rollouts in):
+ *   obs_seq [horizon + 1, n_envs, D] ; transition (t, j) has obs = obs_seq[t + 1, j], pre_obs = obs_seq[t, j]
+ *   (hopper.py:95-97 / half_cheetah.py:60: x_velocity = (obs[:,0] - pre_obs[:,0]) / dt) ;
+ *   reward [horizon, n_envs] ; done [horizon, n_envs] ; sumsq over the action tensor [horizon, n_envs, A].
+ * Equal, bit for bit, to emei_reward_terminal_* on obs = obs_seq[1:], pre_obs = obs_seq[:-1] flattened -- and that
+ * call takes the same kernel whenever pre_obs + k*D == obs (k >= 256): one thread walks the time steps of an env and
+ * carries obs[t][0] in a register, so every observation row is read ONCE (65 / 101 bytes per Hopper / HalfCheetah
+ * transition instead of the 113 / 173 bytes of DRAM traffic a separate strided pre_obs[:,0] column costs).
+ * n_envs * D * sizeof(real) must be a multiple of 16. */
+int emei_reward_terminal_seq_f32(const float* obs_seq, float* reward, uint8_t* done, double* stats, const double* sumsq,
+                                 int64_t n_envs, int64_t horizon, const emei_scoring_params* p, emei_stream_t stream);
+int emei_reward_terminal_seq_f64(const double* obs_seq, double* reward, uint8_t* done, double* stats, const double* sumsq,
+                                 int64_t n_envs, int64_t horizon, const emei_scoring_params* p, emei_stream_t stream);
+
 /* sum of squares of n_elems values, accumulated in double, written to *out (device).
  * Replaces np.sum(np.square(action)) (hopper.py:98, half_cheetah.py:61).  One launch, deterministic:
  * per-CTA partials go to `workspace` and the last CTA adds them in index order (no floating-point

@@ -20,10 +20,12 @@ PURPOSE_ROLLOUT_ACTION = 4
 MASK64 = 0xFFFFFFFFFFFFFFFF
 
 
-def rollout_seeds(seed: int):
-    """(seed_reset, seed_action) exactly as emei_b200.core.EmeiEnv.rollout derives them from reset(seed=)."""
+def rollout_seeds(seed: int, epoch: int = 0):
+    """(seed_reset, seed_action) exactly as emei_b200.core.EmeiEnv.rollout derives them from reset(seed=);
+    ``epoch`` = number of un-seeded reset() calls since that seeded one."""
     seed &= MASK64
-    return (seed * 0x9E3779B97F4A7C15 + 0x5851F42D4C957F2D) & MASK64, (seed * 0xD1B54A32D192ED03 + 0x14057B7EF767814F) & MASK64
+    return ((seed * 0x9E3779B97F4A7C15 + 0x5851F42D4C957F2D + epoch * 0xA0761D6478BD642F) & MASK64,
+            (seed * 0xD1B54A32D192ED03 + 0x14057B7EF767814F + epoch * 0xE7037ED1A0B428DB) & MASK64)
 
 
 PURPOSE_ROLLOUT_RESET = 5
