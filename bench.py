@@ -14,10 +14,16 @@ and secondary bench lines, committed under profiles/):
   c5            scoring 2^26 transitions/GPU (half Hopper, half HalfCheetah) + freeze/unfreeze of a
                 2^26-env cart-pole state buffer per sweep
 
+  c3_*_seq      the same scoring on a trajectory tensor obs_seq[T+1, n, D] (T = 16, n = 2^20): every row read once
+  c2_f64 etc.   --dtype f64 runs c1 / c2 / c3_* / c4 in the float64 reference-exact mode
+
   python bench.py [--gpus N --steps K --warmup W] [--workload W]          # our arm (torchrun for N>1)
   python bench.py --impl reference [--steps K --warmup W] [--workload W]  # CPU arm: the oracle port on host cores
 
-One JSON line on stdout (rank 0).
+One JSON line on stdout (rank 0).  With the default workload the line also carries `secondary`: one compact record
+(value, ms_per_step, roofline, e2e, clocks) per other BASELINE config, measured in the same process under a time box
+(N = 1: c1, c2 in float64, c3 Hopper / HalfCheetah in both layouts, c4, c4 as fused rollouts, c5; N > 1: c4 strong,
+c4 rollouts strong, c5 weak), so that the driver's BENCH / SCALE files see every config.
 """
 import argparse
 import json
@@ -240,21 +246,35 @@ def cpu_rate(kind, sample_units, reps, cores):
 # ==================================================================================================
 # workloads
 # ==================================================================================================
+def _tdtype(args):
+    import torch
+
+    return torch.float64 if args.dtype == "f64" else torch.float32
+
+
 class Workload:
-    key = name = metric = unit = kernel = ""
-    dtype = "f32"
+    key = name = metric = unit = ""
     scaling = "weak"
-    use_graph = True
-    bound = "hbm"  # which roofline bounds the dominant kernel: "hbm" | "issue" (warp-instruction issue)
-    alg_bytes = 0  # algorithmic bytes per unit (SURVEY.md 8d / DESIGN.md 5)
+    use_graph = True  # launch-bound steps: the K launches may be captured in one CUDA graph
+    bound = "hbm"  # which roofline bounds the dominant kernel: "hbm" | "math" (no per-unit HBM traffic to speak of)
+    alg_bytes = 0  # algorithmic bytes per unit (SURVEY.md 8d / DESIGN.md 4), float32
+    alg_bytes_f64 = 0
+    kernel = kernel_f64 = ""
+    # algorithmic math per unit: FP operations (an add, a multiply, an FMA or a divide is ONE op) and
+    # special-function evaluations (sin, cos, rcp/div, sqrt, asin: one MUFU-class op each); None = trivial / not stated
+    alg_fp_ops = alg_sfu_ops = None
+    inst_per_unit = None  # thread-level SASS instructions per unit from ncu (issue utilisation, reported beside the roofline)
     cpu_kind = None  # which oracle routine is the CPU baseline
     cpu_sample = 1 << 20
+    supports_f64 = False
+    e2e_api = None
+    units = 0  # units processed by THIS rank in one step
 
     def __init__(self, args, rank, world, dev):
         self.args, self.rank, self.world, self.dev = args, rank, world, dev
-
-    # units processed by THIS rank in one step
-    units = 0
+        self.f64 = args.dtype == "f64"
+        if self.f64 and not self.supports_f64:
+            raise SystemExit(f"bench.py: workload {self.key} has no float64 mode (the fused rollouts are float32)")
 
     def setup(self):
         raise NotImplementedError
@@ -263,29 +283,51 @@ class Workload:
         raise NotImplementedError
 
     def setup_e2e(self):
-        raise NotImplementedError
+        self.h2d = self.d2h = 0
+        self.e2e_api = None
 
     def step_e2e(self, i):
         raise NotImplementedError
 
-    def config(self):
+    def teardown(self):
+        """drop every device / pinned buffer (the next workload of a `secondary` sweep needs the memory)"""
+        for k in list(self.__dict__):
+            if k not in ("args", "rank", "world", "dev", "f64"):
+                delattr(self, k)
+
+    # ---- config: a pure function of (class, args, world) so that the CPU reference arm prints the SAME dict
+    @classmethod
+    def config(cls, args, world):
         return {}
 
-    def dominant_kernel_ms(self, ms_per_step):
-        """duration of the dominant kernel per launch; default: the whole step is that one kernel."""
-        return ms_per_step
+    @classmethod
+    def units_per_step_total(cls, args, world):
+        """units of one step over all ranks (what the reference arm processes per step)"""
+        raise NotImplementedError
+
+    def bytes_per_unit(self):
+        return self.alg_bytes_f64 if self.f64 else self.alg_bytes
+
+    def kernel_name(self):
+        return self.kernel_f64 if self.f64 else self.kernel
 
 
 class CartPoleStep(Workload):
     """C2 (and, with the IP env, C1): ring of independent batches larger than L2, rotated every launch."""
 
     key, metric, unit = "c2", "env_steps_per_sec", "env-steps/s"
-    name = "ContinuousCartPoleSwingUp batched step, 2^20 envs/GPU, freq_rate=4, float32 (BASELINE configs[1])"
+    title = "ContinuousCartPoleSwingUp batched step, 2^20 envs/GPU, freq_rate=4 (BASELINE configs[1])"
     kernel = "emei::cartpole_step_f32_tma_kernel<IP=0, AK=f32, FR=4, HAS_OBS=0>"
+    kernel_f64 = "emei::cartpole_step_kernel<double, IP=0> (reference-exact mixed arithmetic, -fmad=false)"
     env_id, n_envs, freq_rate, ring = "ContinuousCartPoleSwingUp-v0", 1 << 20, 4, 8
     alg_bytes = 41  # state 16 + action 4 + next 16 + reward 4 + done 1
+    alg_bytes_f64 = 77  # state 32 + action 4 + next 32 + reward 8 + done 1
+    # cartpole.py:48-60 per sub-step: 26 FP ops of which 4 divides, 1 sin + 1 cos; + reward cos and 2 ops, terminal 2 ops
+    alg_fp_ops = 4 * 26 + 4
+    alg_sfu_ops = 4 * (2 + 4) + 1
     cpu_kind = "c2"
-    inst_per_unit = 179.1  # thread-level SASS instructions per env-step = 32 x smsp__inst_executed / envs (packed f32x2: one FFMA2 serves two envs); ncu, profiles/r01_launches_bench_c2.csv
+    supports_f64 = True
+    inst_per_unit = 179.1  # 32 x smsp__inst_executed / envs, packed f32x2 (ncu, profiles/r01_launches_bench_c2.csv)
 
     def synth(self, seed):
         return synth_cartpole(self.n_envs, seed)
@@ -300,8 +342,8 @@ class CartPoleStep(Workload):
         st, act = self.synth(1002 + self.rank)
         self.envs, self.acts = [], []
         for j in range(ring):
-            env = E.make(self.env_id, freq_rate=self.freq_rate, real_time_scale=DT, num_envs=self.n_envs,
-                         dtype=torch.float32, device=self.dev, env_offset=(self.rank * ring + j) * self.n_envs)
+            env = E.make(self.env_id, freq_rate=self.freq_rate, real_time_scale=DT, num_envs=self.n_envs, dtype=_tdtype(self.args),
+                         device=self.dev, env_offset=(self.rank * ring + j) * self.n_envs, copy_outputs=False)
             env.state = np.roll(st, j * 4099, axis=0)
             env._stats = self.envs[0].stats if self.envs else env.stats  # one shared statistics buffer
             self.envs.append(env)
@@ -329,21 +371,30 @@ class CartPoleStep(Workload):
     def step_e2e(self, i):
         self.env0.step_host(self.act_host[i % len(self.act_host)])
 
-    def config(self):
-        ring = len(self.envs)
-        mb = ring * self.n_envs * self.alg_bytes / 1e6
+    @classmethod
+    def config(cls, args, world):
+        ring = args.ring or cls.ring
+        bpu = cls.alg_bytes_f64 if args.dtype == "f64" else cls.alg_bytes
+        mb = ring * cls.n_envs * bpu / 1e6
         return {
-            "envs_per_gpu": self.n_envs, "freq_rate": self.freq_rate, "real_time_scale": DT,
-            "l2_policy": f"inputs larger than L2: ring of {ring} independent {self.n_envs}-env batches ({mb:.0f} MB of step traffic) rotated every launch",
+            "envs_per_gpu": cls.n_envs, "freq_rate": cls.freq_rate, "real_time_scale": DT,
+            "l2_policy": f"inputs larger than L2: ring of {ring} independent {cls.n_envs}-env batches ({mb:.0f} MB of step traffic) rotated every launch",
         }
+
+    @classmethod
+    def units_per_step_total(cls, args, world):
+        return cls.n_envs * world
 
 
 class IPStep(CartPoleStep):
     key = "c1"
-    name = "BoundaryInvertedPendulumSwingUp batched step, 4096 envs, freq_rate=1, float32 (BASELINE configs[0])"
+    title = "BoundaryInvertedPendulumSwingUp batched step, 4096 envs, freq_rate=1 (BASELINE configs[0])"
     kernel = "emei::cartpole_step_f32_small_kernel<IP=1, AK=f32, FR=1, HAS_OBS=1>"
+    kernel_f64 = "emei::cartpole_step_kernel<double, IP=1>"
     env_id, n_envs, freq_rate, ring = "BoundaryInvertedPendulumSwingUp-v0", 4096, 1, 1024
     alg_bytes = 57  # state 16 + action 4 + next state 16 + wrapped obs 16 + reward 4 + done 1
+    alg_bytes_f64 = 109
+    alg_fp_ops, alg_sfu_ops = 26 + 4 + 3, (2 + 4) + 1
     cpu_kind, cpu_sample = "c1", 1 << 20
     inst_per_unit = 202.5  # one env per thread, 128-thread CTAs: profiles/r01_launches_bench_c1.csv
 
@@ -355,7 +406,7 @@ class CartPoleStepLarge(CartPoleStep):
     """The C2 step at 2^24 envs per GPU: launch ramp and drain amortised, the kernel's steady state (recycled TMA ring)."""
 
     key = "c2_large"
-    name = "ContinuousCartPoleSwingUp batched step, 2^24 envs/GPU, freq_rate=4, float32 (C2's kernel at 16x the batch)"
+    title = "ContinuousCartPoleSwingUp batched step, 2^24 envs/GPU, freq_rate=4 (C2's kernel at 16x the batch)"
     n_envs, ring = 1 << 24, 2
     use_graph = False
 
@@ -365,28 +416,29 @@ class I2PStep(CartPoleStep):
     launch), same protocol as C2."""
 
     key = "i2p"
-    name = "BoundaryInvertedDoublePendulumSwingUp batched step, 2^20 envs/GPU, freq_rate=1, float32 (SURVEY 8f rank 3)"
+    title = "BoundaryInvertedDoublePendulumSwingUp batched step, 2^20 envs/GPU, freq_rate=1 (SURVEY 8f rank 3)"
     kernel = "emei::i2p_step_kernel<float>"
+    kernel_f64 = "emei::i2p_step_kernel<double>"
     env_id, n_envs, freq_rate, ring = "BoundaryInvertedDoublePendulumSwingUp-v0", 1 << 20, 1, 8
     alg_bytes = 81  # state 24 + action 4 + next state 24 + observation 24 + reward 4 + done 1
+    alg_bytes_f64 = 157
+    alg_fp_ops = alg_sfu_ops = None  # SURVEY 8d states no operation count for the 3x3 Lagrangian solve
     cpu_kind, cpu_sample = "i2p", 1 << 18
     inst_per_unit = 342.7  # 32 x smsp__inst_executed / envs (ncu, profiles/r01_launches_i2p.csv)
 
     def synth(self, seed):
         return synth_i2p(self.n_envs, seed)
 
-    def setup_e2e(self):
-        self.h2d = self.d2h = 0
-        self.e2e_api = None  # step_host covers the cart-pole / IP / charged-ball engines
-
 
 class Scoring(Workload):
-    """C3: fused get_batch_reward + get_batch_terminal over n transitions resident in HBM (>> L2)."""
+    """C3: get_batch_reward + get_batch_terminal over n transitions resident in HBM (>> L2), through the reference's
+    one-shot signature (obs, pre_obs, action) with pre_obs a SEPARATE array."""
 
     metric, unit = "transitions_per_sec", "transitions/s"
     use_graph = False
     family, n = "hopper", 1 << 24
     env_kwargs = {}
+    supports_f64 = True
 
     def setup(self):
         import torch
@@ -394,12 +446,11 @@ class Scoring(Workload):
         import emei_b200 as E
 
         self.units = self.n
-        self.env = E.make(self.env_id, dtype=torch.float32, device=self.dev, **self.env_kwargs)
+        self.env = E.make(self.env_id, dtype=_tdtype(self.args), device=self.dev, **self.env_kwargs)
         obs, pre, act = synth_scoring(self.n, self.family, 1003 + 17 * self.rank)
         self._host = (obs, pre, act)
-        self.obs, self.pre, self.act = (torch.as_tensor(a).to(self.dev) for a in (obs, pre, act))
+        self.obs, self.pre, self.act = (torch.as_tensor(a).to(self.dev).to(_tdtype(self.args)) for a in (obs, pre, act))
         self.stats = self.env.stats
-        self._ev = []
 
     def step(self, i):
         self.out = self.env.get_batch_reward_terminal(self.obs, self.pre, self.act)
@@ -407,11 +458,12 @@ class Scoring(Workload):
     def setup_e2e(self):
         import torch
 
-        self.h_in = [torch.as_tensor(a).pin_memory() for a in self._host]
-        self.h_r = torch.empty((self.n, 1), dtype=torch.float32).pin_memory()
+        dt = _tdtype(self.args)
+        self.h_in = [torch.as_tensor(a).to(dt).pin_memory() for a in self._host]
+        self.h_r = torch.empty((self.n, 1), dtype=dt).pin_memory()
         self.h_d = torch.empty((self.n, 1), dtype=torch.bool).pin_memory()
         self.h2d = sum(t.numel() * t.element_size() for t in self.h_in)
-        self.d2h = self.h_r.numel() * 4 + self.h_d.numel()
+        self.d2h = self.h_r.numel() * self.h_r.element_size() + self.h_d.numel()
         self.e2e_api = "env.get_batch_reward_terminal(obs, pre_obs, action) with pinned HOST tensors -> reward/terminal copied back to pinned host"
 
     def step_e2e(self, i):
@@ -422,25 +474,117 @@ class Scoring(Workload):
         self.h_d.copy_(d, non_blocking=True)
         torch.cuda.current_stream(self.dev).synchronize()
 
-    def config(self):
-        return {"transitions_per_gpu": self.n, "l2_policy": f"inputs larger than L2 ({self.n * self.alg_bytes / 1e6:.0f} MB per sweep)",
-                "note": "step = emei_sumsq (batch-wide control cost, 1 launch) + fused emei_reward_terminal (1 launch)"}
+    @classmethod
+    def config(cls, args, world):
+        bpu = cls.alg_bytes_f64 if args.dtype == "f64" else cls.alg_bytes
+        return {"transitions_per_gpu": cls.n, "l2_policy": f"inputs larger than L2 ({cls.n * bpu / 1e6:.0f} MB per sweep)",
+                "note": "step = emei_sumsq (batch-wide control cost, 1 launch) + fused emei_reward_terminal (1 launch); the roofline counts the WHOLE step"}
+
+    @classmethod
+    def units_per_step_total(cls, args, world):
+        return cls.n * world
 
 
 class HopperScoring(Scoring):
     key, family, env_id = "c3_hopper", "hopper", "HopperRunning-v0"
-    name = "Hopper get_batch_reward+get_batch_terminal, 2^24 transitions/GPU, terminate_when_unhealthy=False, float32 (BASELINE configs[2])"
-    kernel = "emei::reward_terminal_kernel<float, HOPPER> (+ emei::sumsq_kernel<float>)"
+    title = "Hopper get_batch_reward+get_batch_terminal, 2^24 transitions/GPU, terminate_when_unhealthy=False (BASELINE configs[2])"
+    kernel = "emei::sumsq_kernel<float> + emei::reward_terminal_kernel<float, HOPPER>"
+    kernel_f64 = "emei::sumsq_kernel<double> + emei::reward_terminal_kernel<double, HOPPER>"
     env_kwargs = {"terminate_when_unhealthy": False}
     alg_bytes = 69  # obs 48 + pre_obs[:,0] 4 + action 12 + reward 4 + done 1
+    alg_bytes_f64 = 137
     cpu_kind, cpu_sample = "c3_hopper", 1 << 22
 
 
 class HalfCheetahScoring(Scoring):
     key, family, env_id = "c3_halfcheetah", "halfcheetah", "HalfCheetahRunning-v0"
-    name = "HalfCheetah get_batch_reward+get_batch_terminal, 2^24 transitions/GPU, float32 (BASELINE configs[2])"
-    kernel = "emei::reward_terminal_kernel<float, HALFCHEETAH> (+ emei::sumsq_kernel<float>)"
+    title = "HalfCheetah get_batch_reward+get_batch_terminal, 2^24 transitions/GPU (BASELINE configs[2])"
+    kernel = "emei::sumsq_kernel<float> + emei::reward_terminal_kernel<float, HALFCHEETAH>"
+    kernel_f64 = "emei::sumsq_kernel<double> + emei::reward_terminal_kernel<double, HALFCHEETAH>"
     alg_bytes = 105  # obs 72 + pre_obs[:,0] 4 + action 24 + reward 4 + done 1
+    alg_bytes_f64 = 209
+    cpu_kind, cpu_sample = "c3_halfcheetah", 1 << 22
+
+
+class SeqScoring(Scoring):
+    """C3 on the layout an MBRL scorer holds its imagined rollouts in: obs_seq [T+1, n, D], action [T, n, A]
+    (T = 16, n = 2^20: the same 2^24 transitions).  pre_obs of step t IS obs of step t-1, so a thread that walks the
+    time steps of its env reads every observation row once: no pre_obs traffic at all."""
+
+    T, n_env = 16, 1 << 20
+
+    def setup(self):
+        import torch
+
+        import emei_b200 as E
+
+        self.units = self.n = self.T * self.n_env
+        dt = _tdtype(self.args)
+        self.env = E.make(self.env_id, dtype=dt, device=self.dev, **self.env_kwargs)
+        g = torch.Generator(device=self.dev)
+        g.manual_seed(1003 + 17 * self.rank)
+        d, da = (12, 3) if self.family == "hopper" else (18, 6)
+        seq = torch.randn((self.T + 1, self.n_env, d), device=self.dev, dtype=torch.float32, generator=g)
+        if self.family == "hopper":
+            seq *= torch.tensor([1, 0.4, 0.15] + [1] * 9, device=self.dev)
+            seq[:, :, 1] += 1.25
+        bad = torch.randint(0, seq.numel(), (max(1, seq.numel() // 12000),), device=self.dev, generator=g)
+        seq.view(-1)[bad] = float("nan")  # poisoned rows (SURVEY 8d): 0.1 % of the transitions
+        self.seq = seq.to(dt)
+        self.act = (torch.rand((self.T, self.n_env, da), device=self.dev, generator=g) * 2 - 1).to(dt)
+        self.stats = self.env.stats
+
+    def step(self, i):
+        self.out = self.env.get_batch_reward_terminal_seq(self.seq, self.act)
+
+    def setup_e2e(self):
+        import torch
+
+        self.h_in = [self.seq.cpu().pin_memory(), self.act.cpu().pin_memory()]
+        self.h_r = torch.empty((self.T, self.n_env, 1), dtype=self.seq.dtype).pin_memory()
+        self.h_d = torch.empty((self.T, self.n_env, 1), dtype=torch.bool).pin_memory()
+        self.h2d = sum(t.numel() * t.element_size() for t in self.h_in)
+        self.d2h = self.h_r.numel() * self.h_r.element_size() + self.h_d.numel()
+        self.e2e_api = "env.get_batch_reward_terminal_seq(obs_seq, action) with pinned HOST tensors -> reward/terminal copied back to pinned host"
+
+    def step_e2e(self, i):
+        import torch
+
+        r, d = self.env.get_batch_reward_terminal_seq(*self.h_in)
+        self.h_r.copy_(r, non_blocking=True)
+        self.h_d.copy_(d, non_blocking=True)
+        torch.cuda.current_stream(self.dev).synchronize()
+
+    @classmethod
+    def config(cls, args, world):
+        bpu = cls.alg_bytes_f64 if args.dtype == "f64" else cls.alg_bytes
+        return {"transitions_per_gpu": cls.T * cls.n_env, "layout": f"obs_seq [T+1={cls.T + 1}, n={cls.n_env}, D], action [T, n, A]",
+                "l2_policy": f"inputs larger than L2 ({cls.T * cls.n_env * bpu / 1e6:.0f} MB per sweep)",
+                "note": "step = emei_sumsq (1 launch) + emei_reward_terminal_seq (1 launch); the roofline counts the WHOLE step"}
+
+    @classmethod
+    def units_per_step_total(cls, args, world):
+        return cls.T * cls.n_env * world
+
+
+class HopperSeqScoring(SeqScoring):
+    key, family, env_id = "c3_hopper_seq", "hopper", "HopperRunning-v0"
+    title = "Hopper reward+terminal of imagined rollouts obs_seq[17, 2^20, 12] = 2^24 transitions/GPU, terminate_when_unhealthy=False (BASELINE configs[2], trajectory layout)"
+    kernel = "emei::sumsq_kernel<float> + emei::reward_terminal_seq_kernel<float, HOPPER>"
+    kernel_f64 = "emei::sumsq_kernel<double> + emei::reward_terminal_seq_kernel<double, HOPPER>"
+    env_kwargs = {"terminate_when_unhealthy": False}
+    alg_bytes = 65 + 48 / 16  # obs 48 + action 12 + reward 4 + done 1, + the t = 0 row once per 16 steps
+    alg_bytes_f64 = 129 + 96 / 16
+    cpu_kind, cpu_sample = "c3_hopper", 1 << 22
+
+
+class HalfCheetahSeqScoring(SeqScoring):
+    key, family, env_id = "c3_halfcheetah_seq", "halfcheetah", "HalfCheetahRunning-v0"
+    title = "HalfCheetah reward+terminal of imagined rollouts obs_seq[17, 2^20, 18] = 2^24 transitions/GPU (BASELINE configs[2], trajectory layout)"
+    kernel = "emei::sumsq_kernel<float> + emei::reward_terminal_seq_kernel<float, HALFCHEETAH>"
+    kernel_f64 = "emei::sumsq_kernel<double> + emei::reward_terminal_seq_kernel<double, HALFCHEETAH>"
+    alg_bytes = 101 + 72 / 16
+    alg_bytes_f64 = 201 + 144 / 16
     cpu_kind, cpu_sample = "c3_halfcheetah", 1 << 22
 
 
@@ -448,12 +592,22 @@ class ChargedBall(Workload):
     """C4: 2^26 envs in total, sharded contiguously over the ranks (strong scaling); state updated in place."""
 
     key, metric, unit = "c4", "env_steps_per_sec", "env-steps/s"
-    name = "ChargedBallCentering batched step, 2^26 envs total sharded over the ranks, freq_rate=1, float32 (BASELINE configs[3])"
+    title = "ChargedBallCentering batched step, 2^26 envs total sharded over the ranks, freq_rate=1 (BASELINE configs[3])"
     kernel = "emei::charged_ball_step_f32_kernel<AK=u8>"
+    kernel_f64 = "emei::charged_ball_step_kernel<double, F32FORCE=0>"
     scaling, use_graph = "strong", False
     total = 1 << 26
     alg_bytes = 56  # state in 25 + action 1 (uint8) + state out 25 + reward 4 + done 1
+    alg_bytes_f64 = 108  # state 49 + 1 + 49 + 8 + 1
+    # charged_ball.py:68-82 on the ring: sin, cos of theta before and after the update (4), 1 divide, ~20 FP ops;
+    # reward: 1 sqrt + 1 divide (:158-160)
+    alg_fp_ops, alg_sfu_ops = 22, 4 + 1 + 2
     cpu_kind, cpu_sample = "c4", 1 << 20
+    supports_f64 = True
+
+    @classmethod
+    def _total(cls, args):
+        return 1 << args.total_log2 if args.total_log2 else cls.total
 
     def setup(self):
         import torch
@@ -461,11 +615,11 @@ class ChargedBall(Workload):
         import emei_b200 as E
         from emei_b200.dist import shard_range
 
-        if self.args.total_log2:
-            self.total = 1 << self.args.total_log2
+        self.total = self._total(self.args)
         b, e = shard_range(self.total, self.rank, self.world)
         self.units = e - b
-        self.env = E.make("ChargedBallCentering-v0", num_envs=self.units, dtype=torch.float32, device=self.dev, env_offset=b)
+        self.env = E.make("ChargedBallCentering-v0", num_envs=self.units, dtype=_tdtype(self.args), device=self.dev, env_offset=b,
+                          copy_outputs=False)
         self.env.reset(seed=1004)
         g = torch.Generator(device=self.dev)
         g.manual_seed(1004 + self.rank)
@@ -477,8 +631,6 @@ class ChargedBall(Workload):
         self.env.step(self.acts[i % 4])
 
     def setup_e2e(self):
-        import torch
-
         self.act_host = [a.cpu().pin_memory() for a in self.acts]
         self.env.step_host(self.act_host[0])
         self.h2d, self.d2h = self.env._staging.h2d_bytes, self.env._staging.d2h_bytes
@@ -489,9 +641,16 @@ class ChargedBall(Workload):
     def step_e2e(self, i):
         self.env.step_host(self.act_host[i % 4])
 
-    def config(self):
-        return {"envs_total": self.total, "envs_per_gpu": self.units, "freq_rate": 1,
-                "l2_policy": f"inputs larger than L2 ({self.units * self.alg_bytes / 1e6:.0f} MB per step per GPU)"}
+    @classmethod
+    def config(cls, args, world):
+        tot = cls._total(args)
+        bpu = cls.alg_bytes_f64 if args.dtype == "f64" else cls.alg_bytes
+        return {"envs_total": tot, "envs_per_gpu": tot // world, "freq_rate": 1,
+                "l2_policy": f"inputs larger than L2 ({tot // world * bpu / 1e6:.0f} MB per step per GPU)"}
+
+    @classmethod
+    def units_per_step_total(cls, args, world):
+        return cls._total(args)
 
 
 class ScoringSweep(Workload):
@@ -499,13 +658,14 @@ class ScoringSweep(Workload):
     Hopper + HalfCheetah reward/terminal over 2^25 transitions each, unfreeze()."""
 
     key, metric, unit = "c5", "transitions_per_sec", "transitions/s"
-    name = "MBRL scoring sweep: 2^26 transitions/GPU (half Hopper, half HalfCheetah) reward+terminal + freeze/unfreeze of a 2^26-env cart-pole buffer, float32 (BASELINE configs[4])"
+    title = "MBRL scoring sweep: 2^26 transitions/GPU (half Hopper, half HalfCheetah) reward+terminal + freeze/unfreeze of a 2^26-env cart-pole buffer (BASELINE configs[4])"
     kernel = "emei::reward_terminal_kernel<float, HALFCHEETAH> (dominant), HOPPER, sumsq, snapshot_copy"
     use_graph = False
     n_half, n_env = 1 << 25, 1 << 26
     # per transition: (69 + 105)/2 scoring + 2 x (16 read + 16 write) snapshot bytes per env over n_env == 2*n_half transitions
     alg_bytes = (69 + 105) / 2 + 64
     cpu_kind, cpu_sample = "c3_hopper", 1 << 22
+    e2e_half = 1 << 22  # transitions per family of the host-buffer sample
 
     def setup(self):
         import torch
@@ -515,7 +675,7 @@ class ScoringSweep(Workload):
         self.units = 2 * self.n_half
         self.hop = E.make("HopperRunning-v0", terminate_when_unhealthy=False, dtype=torch.float32, device=self.dev)
         self.chee = E.make("HalfCheetahRunning-v0", dtype=torch.float32, device=self.dev)
-        self.cp = E.make("CartPoleSwingUp-v0", num_envs=self.n_env, dtype=torch.float32, device=self.dev)
+        self.cp = E.make("CartPoleSwingUp-v0", num_envs=self.n_env, dtype=torch.float32, device=self.dev, copy_outputs=False)
         self.cp.reset(seed=1005)
         self.data = []
         for fam in ("hopper", "halfcheetah"):
@@ -530,36 +690,64 @@ class ScoringSweep(Workload):
         self.cp.unfreeze()
 
     def setup_e2e(self):
-        self.h2d = self.d2h = 0
-        self.e2e_api = None
+        import torch
 
-    def config(self):
-        return {"transitions_per_gpu": self.units, "snapshot_envs_per_gpu": self.n_env,
+        m = self.e2e_half
+        self.h_in = [[t[:m].cpu().pin_memory() for t in fam] for fam in self.data]
+        self.h_out = [(torch.empty((m, 1), dtype=torch.float32).pin_memory(), torch.empty((m, 1), dtype=torch.bool).pin_memory()) for _ in range(2)]
+        self.h2d = sum(t.numel() * t.element_size() for fam in self.h_in for t in fam)
+        self.d2h = 2 * m * 5
+        self.e2e_units = 2 * m
+        self.e2e_api = (f"freeze(); hopper / halfcheetah get_batch_reward_terminal on pinned HOST tensors ({m} transitions each: a bounded "
+                        "sample of the sweep, the rate is per transition) -> results copied back to pinned host; unfreeze()")
+
+    def step_e2e(self, i):
+        import torch
+
+        self.cp.freeze()
+        for env, h_in, (h_r, h_d) in zip((self.hop, self.chee), self.h_in, self.h_out):
+            r, d = env.get_batch_reward_terminal(*h_in)
+            h_r.copy_(r, non_blocking=True)
+            h_d.copy_(d, non_blocking=True)
+        self.cp.unfreeze()
+        torch.cuda.current_stream(self.dev).synchronize()
+
+    @classmethod
+    def config(cls, args, world):
+        return {"transitions_per_gpu": 2 * cls.n_half, "snapshot_envs_per_gpu": cls.n_env,
                 "l2_policy": "inputs larger than L2 (10 GB per sweep)"}
+
+    @classmethod
+    def units_per_step_total(cls, args, world):
+        return 2 * cls.n_half * world
 
 
 class CartPoleRollout(Workload):
     """the collection loop (zoo/util.py:33-93) as ONE launch per `horizon` env-steps: state,
     TimeLimit counter and episode return in registers, in-kernel auto-reset and uniform random policy.  No
-    per-step HBM traffic (24 B per env per launch), so the bound is warp-instruction issue."""
+    per-step HBM traffic (24 B per env per launch), so the bound is math."""
 
     key, metric, unit = "rollout", "env_steps_per_sec", "env-steps/s"
-    name = "ContinuousCartPoleSwingUp fused rollout, 2^20 envs/GPU x horizon steps per launch, freq_rate=4, in-kernel random policy + TimeLimit(1000) + auto-reset, float32 (SURVEY 8f rank 1)"
+    title = "ContinuousCartPoleSwingUp fused rollout, 2^20 envs/GPU x horizon steps per launch, freq_rate=4, in-kernel random policy + TimeLimit(1000) + auto-reset (SURVEY 8f rank 1)"
     kernel = "emei::rollout_f32_kernel<CartPoleDyn<IP=0, AK=f32, FR=4>, RECORD=0>"
     env_id, n_envs, freq_rate = "ContinuousCartPoleSwingUp-v0", 1 << 20, 4
-    use_graph, bound = False, "issue"
+    use_graph, bound = False, "math"
     record = False
-    alg_bytes = 0.0  # set in setup(): per env-step
-    inst_per_unit = 247.1  # thread-level SASS instructions per env-step incl. divergent in-kernel resets (32 x smsp__inst_executed / env-steps; ncu, profiles/r01_launches_rollout*.csv)
+    alg_fp_ops, alg_sfu_ops = CartPoleStep.alg_fp_ops, CartPoleStep.alg_sfu_ops
+    inst_per_unit = 247.1  # thread-level SASS instructions per env-step incl. divergent in-kernel resets (ncu, profiles/r01_launches_rollout*.csv)
     cpu_kind = "c2"
     e2e_max_steps = 5
+
+    @classmethod
+    def _horizon(cls, args):
+        return args.horizon if args.horizon_set else (32 if cls.record else 100)
 
     def setup(self):
         import torch
 
         import emei_b200 as E
 
-        self.T = self.args.horizon
+        self.T = self._horizon(self.args)
         self.units = self.n_envs * self.T
         self.env = E.make(self.env_id, freq_rate=self.freq_rate, real_time_scale=DT, num_envs=self.n_envs,
                           dtype=torch.float32, device=self.dev, env_offset=self.rank * self.n_envs)
@@ -574,6 +762,8 @@ class CartPoleRollout(Workload):
     def setup_e2e(self):
         import torch
 
+        if self.record:
+            return Workload.setup_e2e(self)
         rng = np.random.default_rng(1006 + self.rank)
         self.act_host = [torch.as_tensor(rng.uniform(-1, 1, size=(self.T, self.n_envs)).astype(np.float32)).pin_memory() for _ in range(2)]
         self.h2d = self.act_host[0].numel() * 4
@@ -584,11 +774,17 @@ class CartPoleRollout(Workload):
         out = self.env.rollout(self.T, actions=self.act_host[i % 2])
         self.info = self.env.rollout_info(out["stats"])
 
-    def config(self):
-        return {"envs_per_gpu": self.n_envs, "horizon": self.T, "freq_rate": self.freq_rate, "max_episode_steps": 1000,
-                "records": self.record,
+    @classmethod
+    def config(cls, args, world):
+        T = cls._horizon(args)
+        return {"envs_per_gpu": cls.n_envs, "horizon": T, "freq_rate": cls.freq_rate, "max_episode_steps": 1000,
+                "records": cls.record,
                 "l2_policy": "no reuse to defeat: every env's state is read once and written once per launch"
-                             + (f"; records are {self.units * 42 / 1e6:.0f} MB of fresh writes per launch" if self.record else "")}
+                             + (f"; records are {cls.n_envs * T * 42 / 1e6:.0f} MB of fresh writes per launch" if cls.record else "")}
+
+    @classmethod
+    def units_per_step_total(cls, args, world):
+        return cls.n_envs * cls._horizon(args) * world
 
 
 class CartPoleRolloutRecord(CartPoleRollout):
@@ -596,34 +792,34 @@ class CartPoleRolloutRecord(CartPoleRollout):
     observations/next_observations [T,n,4], actions/rewards [T,n], dones/timeouts u8[T,n] = 42 B per env-step."""
 
     key = "rollout_rec"
-    name = CartPoleRollout.name.replace("fused rollout", "fused rollout + transition records (dataset layout)")
+    title = CartPoleRollout.title.replace("fused rollout", "fused rollout + transition records (dataset layout)")
     kernel = "emei::rollout_f32_kernel<CartPoleDyn<IP=0, AK=f32, FR=4>, RECORD=1>"
     record = True
-    inst_per_unit = 289.9  # (ncu, profiles/r01_launches_rollout_rec.csv) t_issue = 0.26 ms > t_hbm = 0.22 ms (42 B/env-step) at 2^25 env-steps per launch: still issue-bound
-
-    def setup(self):
-        if not self.args.horizon_set:
-            self.args.horizon = 32
-        super().setup()
-
-    def setup_e2e(self):
-        self.h2d = self.d2h = 0
-        self.e2e_api = None
+    inst_per_unit = 289.9  # ncu, profiles/r01_launches_rollout_rec.csv
 
 
 class ChargedBallRollout(Workload):
     """C4 as BASELINE words it ("rollouts, 64M envs x 200 steps"): ONE launch advances every env of the shard by
     `horizon` steps with the state in registers (emei_charged_ball_rollout_f32), in-kernel Bernoulli(1/2) policy,
-    TimeLimit(500) + auto-reset.  HBM is touched once per env per launch, so the bound is warp-instruction issue."""
+    TimeLimit(500) + auto-reset.  HBM is touched once per env per launch, so the bound is math."""
 
     key, metric, unit = "c4_rollout", "env_steps_per_sec", "env-steps/s"
-    name = "ChargedBallCentering fused rollouts, 2^26 envs total sharded over the ranks x 200 steps per launch, freq_rate=1, float32 (BASELINE configs[3])"
+    title = "ChargedBallCentering fused rollouts, 2^26 envs total sharded over the ranks x 200 steps per launch, freq_rate=1 (BASELINE configs[3])"
     kernel = "emei::rollout_f32_kernel<ChargedBallDyn<u8>, RECORD=0>"
-    scaling, use_graph, bound = "strong", False, "issue"
+    scaling, use_graph, bound = "strong", False, "math"
     total = 1 << 26
-    inst_per_unit = 166.0  # warp-level SASS instructions per env-step, all three divergent paths issued (ncu smsp__inst_executed, profiles/r01_launches_c4_rollout.csv)
+    alg_fp_ops, alg_sfu_ops = ChargedBall.alg_fp_ops, ChargedBall.alg_sfu_ops
+    inst_per_unit = 166.0  # warp-level SASS instructions per env-step, all three divergent paths issued (ncu, profiles/r01_launches_c4_rollout.csv)
     cpu_kind, cpu_sample = "c4", 1 << 20
     e2e_max_steps = 5
+
+    @classmethod
+    def _total(cls, args):
+        return 1 << args.total_log2 if args.total_log2 else cls.total
+
+    @classmethod
+    def _horizon(cls, args):
+        return args.horizon if args.horizon_set else 200
 
     def setup(self):
         import torch
@@ -631,9 +827,8 @@ class ChargedBallRollout(Workload):
         import emei_b200 as E
         from emei_b200.dist import shard_range
 
-        if self.args.total_log2:
-            self.total = 1 << self.args.total_log2
-        self.T = self.args.horizon if self.args.horizon_set else 200
+        self.total = self._total(self.args)
+        self.T = self._horizon(self.args)
         b, e = shard_range(self.total, self.rank, self.world)
         self.n = e - b
         self.units = self.n * self.T
@@ -661,42 +856,82 @@ class ChargedBallRollout(Workload):
         out = self.env.rollout(self.Te, actions=self.act_host[i % 2])
         self.info = self.env.rollout_info(out["stats"])
 
-    def config(self):
-        return {"envs_total": self.total, "envs_per_gpu": self.n, "horizon": self.T, "freq_rate": 1, "max_episode_steps": 500,
-                "l2_policy": f"no reuse to defeat: {self.n * 37 / 1e6:.0f} MB of state read once and written once per launch"}
+    @classmethod
+    def config(cls, args, world):
+        tot = cls._total(args)
+        return {"envs_total": tot, "envs_per_gpu": tot // world, "horizon": cls._horizon(args), "freq_rate": 1, "max_episode_steps": 500,
+                "l2_policy": f"no reuse to defeat: {tot // world * 37 / 1e6:.0f} MB of state read once and written once per launch"}
+
+    @classmethod
+    def units_per_step_total(cls, args, world):
+        return cls._total(args) * cls._horizon(args)
 
 
-WORKLOADS = {w.key: w for w in (IPStep, CartPoleStep, CartPoleStepLarge, I2PStep, HopperScoring, HalfCheetahScoring, ChargedBall, ScoringSweep,
-                                CartPoleRollout, CartPoleRolloutRecord, ChargedBallRollout)}
+WORKLOADS = {w.key: w for w in (IPStep, CartPoleStep, CartPoleStepLarge, I2PStep, HopperScoring, HalfCheetahScoring, HopperSeqScoring,
+                                HalfCheetahSeqScoring, ChargedBall, ScoringSweep, CartPoleRollout, CartPoleRolloutRecord, ChargedBallRollout)}
+
+
+def workload_name(W, args):
+    return W.title + (", float64 reference-exact mode" if args.dtype == "f64" else ", float32")
+
+
+def full_config(W, args, world):
+    cfg = {"workload": workload_name(W, args)}
+    cfg.update(W.config(args, world))
+    return cfg
 
 
 # ==================================================================================================
 # reference arm
 # ==================================================================================================
+def cpu_literal(workload):
+    """The reference-literal CPU number: the unmodified reference's scalar env.step loop, timed in
+    the BUILD container by scripts/time_reference_literal.py (the GPU box has no reference tree), carried as a constant."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "cpu_literal.json")))
+        w = d["workloads"].get({"c1": "c1_cartpole_counterpart"}.get(workload, workload))
+        if w is None:
+            return None
+        return {"one_core": w["one_core"], "all_cores": w["all_cores"], "processes": w["processes"], "unit": d["unit"],
+                "env": w["env"], "freq_rate": w["freq_rate"], "kind": "reference-literal, measured in the build container (NOT on this box)",
+                "provenance": f"{d['script']} on {d['cpu']} ({d['cores_available']} cores), {d['when']}: {d['what']}"}
+    except Exception:
+        return None
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    world = max(1, args.gpus)
     W = WORKLOADS[args.workload]
     cores = host_cores()
     kind = W.cpu_kind
-    rate1, _ = cpu_rate(kind, 1 << 14, 1, 1)  # calibrate, then size the per-step sample for ~100 s in total
+    # every step processes the units the GPU arm's step processes (all ranks), unless that exceeds the time box of
+    # ~100 s for the whole run: then a bounded sample of it, stated in cpu_baseline.sample
+    rate1, _ = cpu_rate(kind, 1 << 14, 1, 1)
     total_steps = args.steps + args.warmup
-    sample = int(min(W.cpu_sample * 4, max(1 << 12, rate1 * cores * 0.6 * 100.0 / total_steps)))
+    want = W.units_per_step_total(args, world)
+    cap = int(max(1 << 12, rate1 * cores * 0.6 * 100.0 / total_steps))
+    sample = int(min(want, cap, W.cpu_sample * 16))
     sample -= sample % cores
     if args.warmup:
         cpu_rate(kind, sample, args.warmup, cores)
     rate, wall = cpu_rate(kind, sample, args.steps, cores)
-    desc = f"{sample} units/step x {args.steps} steps of the {cpu_port_desc(kind)}, {cores} processes"
+    desc = (f"{sample} units/step ({'the whole step' if sample >= want - cores else f'a bounded sample of the {want}-unit step'}) x {args.steps} "
+            f"steps of the {cpu_port_desc(kind)}, {cores} processes")
     line = {
         "impl": "reference", "metric": W.metric, "value": rate, "unit": W.unit, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps, "higher_is_better": True, "scaling": W.scaling,
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": W.name, "sample_units_per_step": sample},
+        "config": full_config(W, args, world),
         "cpu_baseline": {"value": rate, "unit": W.unit, "cores": cores, "kind": "port", "sample": desc},
         "e2e": {"value": rate, "unit": W.unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    lit = cpu_literal(args.workload)
+    if lit is not None:
+        line["cpu_baseline_literal"] = lit
     emit_json_line(line)
 
 
@@ -704,7 +939,8 @@ def run_reference(args):
 # GPU arm
 # ==================================================================================================
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    """nvidia-smi clocks / throttle reasons sampled for the whole run (B200_PROFILING.md); a workload's record is the
+    slice of samples taken while its timed regions ran."""
 
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
@@ -722,16 +958,18 @@ class ClockSampler(threading.Thread):
             for ln in self.proc.stdout:
                 if self.stop_flag:
                     break
-                self.rows.append([c.strip() for c in ln.split(",")])
+                self.rows.append((time.monotonic(), [c.strip() for c in ln.split(",")]))
         except Exception:
             pass
 
-    def finish(self):
-        self.stop_flag = True
-        if self.proc is not None:
-            self.proc.terminate()
+    def count(self):
+        return len(self.rows)
+
+    def summary(self, t0=None, t1=None):
         sm, mx, reasons = [], 0, set()
-        for r in self.rows:
+        for ts, r in list(self.rows):
+            if (t0 is not None and ts < t0) or (t1 is not None and ts > t1):
+                continue
             try:
                 sm.append(float(r[0]))
                 mx = max(mx, float(r[1]))
@@ -741,6 +979,11 @@ class ClockSampler(threading.Thread):
             except (ValueError, IndexError):
                 continue
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+
+    def finish(self):
+        self.stop_flag = True
+        if self.proc is not None:
+            self.proc.terminate()
 
 
 def measured_peaks():
@@ -762,41 +1005,79 @@ def measured_math_peaks():
         return None
 
 
-def measured_traffic(workload):
-    """dram bytes per launch of the dominant kernel from the committed ncu --set full capture (profiles/traffic.json,
-    written by scripts/make_traffic_json.py); None when there is no capture for this workload."""
+def measured_traffic(workload, f64):
+    """dram bytes per launch of the step from the committed ncu captures (profiles/traffic.json, written by
+    scripts/make_traffic_json.py); None when there is no capture for this workload."""
     try:
-        return json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(workload)
+        return json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(workload + ("_f64" if f64 else ""))
     except Exception:
         return None
 
 
-def run_ours(args):
+class Ctx:
+    def __init__(self, rank, world, local, dev, sampler):
+        self.rank, self.world, self.local, self.dev, self.sampler = rank, world, local, dev, sampler
+
+
+def math_model(wl, units, seconds, sm_mhz, peak_gbs):
+    """The north star's second bound from ALGORITHMIC operation counts, not from the kernel's own
+    instruction count: t_fp32 = FP ops / (148 SMs x 128 lanes x clock), t_sfu = special-function evaluations /
+    (148 x 16 x clock) -- for float64: the measured FP64 peak.  Issue utilisation (the kernel's own instructions against
+    the issue peak) is reported beside it as a utilisation, not as a roofline."""
+    if wl.alg_fp_ops is None:
+        return None
+    mp = measured_math_peaks() or {}
+    clock = sm_mhz * 1e6
+    if wl.f64:
+        fp_peak = float(mp.get("fp64_tflops", 37.0)) * 1e12 / 2.0  # FMA-class FP64 operations per second
+        # a float64 sin or cos is ~60 FMA-class operations (CUDA libm, Payne-Hanek aside); divides / sqrt ~10
+        fp_ops = wl.alg_fp_ops + 60.0 * (wl.alg_sfu_ops or 0)
+        t_fp, t_sfu = fp_ops * units / fp_peak, 0.0
+        peaks = {"fp64_ops_per_s": fp_peak, "source": "profiles/math_peaks.json fp64_tflops / 2 (tools/f2bench on the B200 box)",
+                 "fp64_ops_per_unit": fp_ops, "note": "special functions counted as 60 FP64 operations each (libm-grade evaluation)"}
+    else:
+        fp_peak, sfu_peak = 148 * 128 * clock, 148 * 16 * clock
+        t_fp, t_sfu = wl.alg_fp_ops * units / fp_peak, (wl.alg_sfu_ops or 0) * units / sfu_peak
+        peaks = {"fp32_lane_ops_per_s": fp_peak, "sfu_ops_per_s": sfu_peak, "source": f"148 SMs x 128 FP32 lanes (16 SFU lanes) x {sm_mhz:.0f} MHz",
+                 "measured": {k: mp[k] for k in ("fp32_tflops", "mufu_rcp_per_s", "mufu_sin_per_s") if k in mp}}
+    t_hbm = wl.bytes_per_unit() * units / (peak_gbs * 1e9)
+    t_math = max(t_fp, t_sfu)
+    out = {
+        "fp_ops_per_unit": wl.alg_fp_ops, "sfu_ops_per_unit": wl.alg_sfu_ops, "t_fp_us": t_fp * 1e6, "t_sfu_us": t_sfu * 1e6,
+        "t_math_us": t_math * 1e6, "t_hbm_us": t_hbm * 1e6, "slower_bound": "math" if t_math > t_hbm else "hbm",
+        "frac_of_slower_bound": max(t_math, t_hbm) / seconds, "peaks": peaks,
+        "source": "operation counts of SURVEY.md 8(d): the reference's arithmetic as written (cartpole.py:48-60, charged_ball.py:68-82), not this kernel's instruction stream",
+    }
+    if wl.inst_per_unit and not wl.f64:
+        issue_peak = 148 * 4 * clock
+        out["issue_utilisation"] = {"thread_inst_per_unit": wl.inst_per_unit, "value": wl.inst_per_unit * units / 32.0 / seconds / issue_peak,
+                                    "note": "this kernel's own warp instructions (ncu smsp__inst_executed, profiles/) / (148 SMs x 4 schedulers x clock): a utilisation, not a roofline"}
+    return out
+
+
+def measure(wl, ctx, K, W, args, want_e2e=True):
+    """One workload: W warm-up steps, exactly K timed steps (barrier + synchronize on both sides, CUDA events on the
+    launching stream, max over ranks), the dominant-kernel roofline, the end-to-end leg.  Returns the record."""
     import torch
     import torch.distributed as dist
 
     from emei_b200 import _lib
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device; emei_b200 has no CPU fallback")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # NCCL's banner must not share stdout with the JSON line
-        dist.init_process_group("nccl", device_id=dev)
-    K, W = args.steps, max(args.warmup, 3)
-    wl = WORKLOADS[args.workload](args, rank, world, dev)
+    rank, world, dev, sampler = ctx.rank, ctx.world, ctx.dev, ctx.sampler
     wl.setup()
-
     for i in range(W):
         wl.step(i)
     torch.cuda.synchronize()
+    launch_mode = args.launch
+    if launch_mode == "auto":
+        # measured (profiles/r02_kbench_c2_variants.txt): at K = 20 the graph runs 9.9 us per step, 20 plain stream
+        # launches queued behind a spinning kernel 10.5 us
+        launch_mode = "graph" if wl.use_graph else "stream"
+    if not wl.use_graph:
+        launch_mode = "stream"
     launches0 = _lib.launch_count
     graph = None
-    if wl.use_graph:  # launch-bound steps: K launches captured once, replayed as one graph
+    if launch_mode == "graph":  # launch-bound steps: K launches captured once, replayed as one graph
         graph = torch.cuda.CUDAGraph()
         side = torch.cuda.Stream(dev)
         with torch.cuda.stream(side):
@@ -804,20 +1085,19 @@ def run_ours(args):
                 for i in range(K):
                     wl.step(i)
         launches = _lib.launch_count - launches0
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-        time.sleep(0.3)
-    # warm the instantiated graph / the step, and keep the GPU under load until nvidia-smi has delivered its first
-    # samples (it needs a few hundred ms to start; a 4 ms C1 region would otherwise end before the first one)
+    # warm the instantiated graph / the step, and keep the GPU under load until nvidia-smi has delivered samples
+    # (it needs a few hundred ms to start; a 0.2 ms region would otherwise end before the first one)
+    t_clock0 = time.monotonic()
+    n0 = sampler.count() if sampler is not None else 0
     t_warm = time.perf_counter()
     while True:
         if graph is not None:
             graph.replay()
         else:
-            wl.step(0)
+            for i in range(min(K, 8)):
+                wl.step(i)
         torch.cuda.synchronize()
-        if rank != 0 or len(sampler.rows) >= 3 or time.perf_counter() - t_warm > 1.5:
+        if sampler is None or sampler.count() - n0 >= 3 or time.perf_counter() - t_warm > 1.5:
             break
     _lib.call("emei_stats_reset", wl.stats.data_ptr(), torch.cuda.current_stream(dev).cuda_stream, launches=0)
     launches0 = _lib.launch_count
@@ -825,10 +1105,12 @@ def run_ours(args):
         dist.barrier()
     torch.cuda.synchronize()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    if graph is not None:
-        # keep the device busy for ~0.1 ms while the host submits the graph, so that the events bracket the K steps
-        # and not the host's graph-launch latency (~30 us: 15 % of a 20-step C2 region, nothing at K = 2000)
-        torch.cuda._sleep(200_000)
+    if wl.use_graph:
+        # launch-bound steps: keep the device busy while the host submits the work, so that the events bracket the K
+        # steps and not the host's submission latency (graph: ~30 us; K direct step() calls: ~25 us each)
+        cyc = args.presleep if args.presleep >= 0 else (200_000 if graph is not None else 400_000 + 80_000 * K)
+        if cyc > 0:
+            torch.cuda._sleep(int(cyc))
     ev0.record()
     if graph is not None:
         graph.replay()
@@ -851,18 +1133,13 @@ def run_ours(args):
     ms_total = float(t.item())
     ms_per_step = ms_total / K
     value = float(units.item()) * K / (ms_total * 1e-3)
-
-    # ---------------- dominant-kernel duration for the roofline (CUDA events around that kernel alone)
-    kern_ms = ms_per_step
-    if not wl.use_graph and hasattr(wl, "env") and args.workload.startswith("c3"):
-        from emei_b200 import engine
-
-        kern_ms = engine.time_fused_scoring(wl.env, wl.obs, wl.pre, wl.act, reps=max(3, min(K, 10)))
+    graph = None
 
     # ---------------- e2e: host inputs in, host results out, every step, through the public API
     e2e = None
-    wl.setup_e2e()
-    if wl.e2e_api is not None:
+    if want_e2e:
+        wl.setup_e2e()
+    if want_e2e and wl.e2e_api is not None:
         e2e_steps = max(3, min(K, args.e2e_steps))
         e2e_steps = min(e2e_steps, getattr(wl, "e2e_max_steps", e2e_steps))
         for i in range(getattr(wl, "e2e_warmup", 2)):  # untimed: first-use work (step_host captures one CUDA graph per
@@ -886,77 +1163,140 @@ def run_ours(args):
             "value": e2e_units * e2e_steps / (float(te.item()) * 1e-3), "unit": wl.unit,
             "h2d_bytes_per_step": wl.h2d, "d2h_bytes_per_step": wl.d2h, "steps": e2e_steps, "api": wl.e2e_api,
         }
-    clocks = sampler.finish() if rank == 0 else None
+    t_clock1 = time.monotonic()
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+        return None
 
     peak, peak_src, sm_mhz = measured_peaks()
-    achieved = wl.alg_bytes * wl.units / (kern_ms * 1e-3) / 1e9
+    step_s = ms_per_step * 1e-3
+    bpu = wl.bytes_per_unit()
+    achieved = bpu * wl.units / step_s / 1e9
     roofline = {
         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-        "peak_source": peak_src, "algorithmic_bytes_per_unit": wl.alg_bytes, "kernel": wl.kernel,
-        "kernel_ms_per_launch": kern_ms,
-        "note": "duration = CUDA-event time of the dominant kernel per launch"
-                + (" (timed region / launches, inter-launch gaps included)" if wl.use_graph else ""),
+        "peak_source": peak_src, "algorithmic_bytes_per_unit": bpu, "kernel": wl.kernel_name(),
+        "kernel_ms_per_launch": ms_per_step,
+        "note": "duration = CUDA-event time of ONE WHOLE STEP (timed region / steps: every kernel of the step and the gaps between launches included)",
     }
-    ipu = getattr(wl, "inst_per_unit", None)
-    if wl.bound == "issue":  # no per-unit HBM traffic to speak of: the roofline is warp-instruction issue
-        issue_peak = 148 * 4 * sm_mhz * 1e6
-        ach = ipu * wl.units / 32.0 / (kern_ms * 1e-3)
+    mm = math_model(wl, wl.units, step_s, sm_mhz, peak)
+    if wl.bound == "math" and mm is not None:  # no per-unit HBM traffic to speak of: the roofline is the algorithmic math
+        binding = "sfu" if mm["t_sfu_us"] >= mm["t_fp_us"] else "fp32"
+        ops = wl.alg_sfu_ops if binding == "sfu" else wl.alg_fp_ops
+        pk = mm["peaks"]["sfu_ops_per_s" if binding == "sfu" else "fp32_lane_ops_per_s"]
         roofline = {
-            "bound": "issue", "achieved": ach / 1e9, "peak": issue_peak / 1e9, "unit": "G warp-inst/s", "frac": ach / issue_peak,
-            "traffic": None, "peak_source": f"148 SMs x 4 schedulers x {sm_mhz:.0f} MHz (MEASURED_PEAKS.json sm_max_mhz), 1 warp instruction per scheduler per clock",
-            "warp_inst_per_unit": ipu, "kernel": wl.kernel, "kernel_ms_per_launch": kern_ms,
-            "hbm": {"algorithmic_bytes_per_unit": wl.alg_bytes, "achieved_gbs": achieved, "frac_of_hbm_peak": achieved / peak},
-            "note": "duration = CUDA-event time per launch; instruction count per env-step from ncu smsp__inst_executed (profiles/)",
+            "bound": "math", "achieved": ops * wl.units / step_s / 1e12, "peak": pk / 1e12, "unit": f"T {binding} op/s (algorithmic)",
+            "frac": mm["t_math_us"] * 1e-6 / step_s, "traffic": None, "kernel": wl.kernel_name(), "kernel_ms_per_launch": ms_per_step,
+            "binding_unit": binding, "math": mm,
+            "hbm": {"algorithmic_bytes_per_unit": bpu, "achieved_gbs": achieved, "frac_of_hbm_peak": achieved / peak},
+            "note": "duration = CUDA-event time per launch; operations = SURVEY 8(d)'s algorithmic counts per env-step x env-steps",
         }
-    elif ipu:  # the second roofline of the north star: warp-instruction issue (148 SMs x 4 schedulers x clock)
-        issue_peak = 148 * 4 * sm_mhz * 1e6
-        t_math = ipu * wl.units / 32.0 / issue_peak
-        t_hbm = wl.alg_bytes * wl.units / (peak * 1e9)
-        roofline["math"] = {
-            "warp_inst_per_unit": ipu, "issue_peak_warp_inst_per_s": issue_peak, "t_math_us": t_math * 1e6,
-            "t_hbm_us": t_hbm * 1e6, "slower_bound": "math" if t_math > t_hbm else "hbm",
-            "frac_of_slower_bound": max(t_math, t_hbm) / (kern_ms * 1e-3),
-        }
-    mp = measured_math_peaks()
-    if mp is not None and ipu:
-        tgt = roofline["math"] if "math" in roofline else roofline
-        tgt["measured_math_peaks"] = {k: mp[k] for k in ("fp32_tflops", "fp64_tflops", "mufu_rcp_per_s", "mufu_sin_per_s") if k in mp}
-        tgt["measured_math_peaks"]["source"] = "profiles/math_peaks.json (tools/f2bench on the B200 box)"
-    tr = measured_traffic(args.workload)
+    elif mm is not None:
+        roofline["math"] = mm
+    tr = measured_traffic(wl.key, wl.f64)
     if tr is not None:
         roofline["traffic"] = tr["bytes_per_launch"]
-        roofline["traffic_source"] = f"{tr['source']}: dram__bytes_read.sum + dram__bytes_write.sum of {tr['kernel'][:60]}... per launch (ncu --set full, cold L2; writes may still sit in the 126 MB L2 when the launch ends)"
-        roofline["algorithmic_bytes_per_launch"] = wl.alg_bytes * wl.units
-        if not wl.use_graph and wl.bound == "hbm":  # kernels much larger than L2: the capture's DRAM bytes at this run's duration
-            roofline["dram_gbs_by_traffic"] = tr["bytes_per_launch"] / (kern_ms * 1e-3) / 1e9
-            roofline["dram_frac_by_traffic"] = roofline["dram_gbs_by_traffic"] / peak
-    cfg = {"workload": wl.name}
-    cfg.update(wl.config())
-    cfg["launch"] = (f"K={K} steps captured in one CUDA graph (programmatic dependent launches), replayed once" if wl.use_graph
-                     else f"K={K} steps launched back to back on one stream") + "; CUDA events on the launching stream"
-    cfg["parallelism"] = f"batch sharded over {world} rank(s), no data-path collective; NCCL all-reduce of the 2-double statistics at the end"
-    line = {
+        roofline["traffic_source"] = tr.get("note") or f"{tr['source']}: dram__bytes_read.sum + dram__bytes_write.sum per step (ncu)"
+        roofline["algorithmic_bytes_per_launch"] = bpu * wl.units
+    cfg = full_config(type(wl), args, world)
+    protocol = {
+        "launch": (f"K={K} steps captured in one CUDA graph (programmatic dependent launches), replayed once" if launch_mode == "graph"
+                   else f"K={K} step() calls launched back to back on one stream" + (" behind a spinning kernel (the device never waits for the host)" if wl.use_graph else ""))
+                  + "; CUDA events on the launching stream",
+        "parallelism": f"batch sharded over {world} rank(s), no data-path collective; NCCL all-reduce of the 2-double statistics at the end",
+    }
+    rec = {
         "metric": wl.metric, "value": value, "unit": wl.unit, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": wl.scaling, "vs_baseline": None,
-        "dtype": wl.dtype, "data": "synthetic", "config": cfg, "roofline": roofline,
-        "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+        "dtype": "f64" if wl.f64 else "f32", "data": "synthetic", "config": cfg, "protocol": protocol, "roofline": roofline,
+        "e2e": e2e, "gpu_launches": launches,
+        "clocks": sampler.summary(t_clock0, t_clock1) if sampler is not None else None,
     }
+    return rec
+
+
+SECONDARY_N1 = [("c1", "f32"), ("c2_f64", "f64"), ("c3_hopper", "f32"), ("c3_halfcheetah", "f32"), ("c3_hopper_seq", "f32"),
+                ("c3_halfcheetah_seq", "f32"), ("c4", "f32"), ("c4_rollout", "f32"), ("c5", "f32")]
+SECONDARY_MULTI = [("c4", "f32"), ("c4_rollout", "f32"), ("c5", "f32")]
+
+
+def run_ours(args):
+    import copy
+    import gc
+
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; emei_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # NCCL's banner must not share stdout with the JSON line
+        dist.init_process_group("nccl", device_id=dev)
+    t_start = time.monotonic()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler is not None:
+        sampler.start()
+        time.sleep(0.3)
+    ctx = Ctx(rank, world, local, dev, sampler)
+    K, W = args.steps, max(args.warmup, 3)
+    wl = WORKLOADS[args.workload](args, rank, world, dev)
+    line = measure(wl, ctx, K, W, args)
     # ---------------- CPU baseline on this box's host cores (bounded sample; oracle = the thing timed beside us)
-    if world == 1 and not args.no_cpu:
+    if rank == 0 and world == 1 and not args.no_cpu:
         n_s = wl.cpu_sample
-        # a bounded sample worth ~10 s of one core: calibrate with one pass, then size the pass count
-        _, wall0 = cpu_rate(wl.cpu_kind, n_s, 1, 1)
+        _, wall0 = cpu_rate(wl.cpu_kind, n_s, 1, 1)  # calibrate with one pass, then size the pass count for ~10 s of one core
         reps = int(max(2, min(200, round(10.0 / max(wall0, 1e-3)))))
         rate1, wall1 = cpu_rate(wl.cpu_kind, n_s, reps, 1)
         line["cpu_baseline"] = {
             "value": rate1, "unit": wl.unit, "cores": 1, "kind": "port",
             "sample": f"{n_s} units x {reps} passes of the {cpu_port_desc(wl.cpu_kind)}, {wall1:.1f} s",
         }
-    emit_json_line(line)
+    if rank == 0:
+        lit = cpu_literal(args.workload)
+        if lit is not None:
+            line["cpu_baseline_literal"] = lit
+    wl.teardown()
+    del wl
+    # ---------------- the other BASELINE configs, same process, compact records, time-boxed
+    if args.secondary:
+        sec = {}
+        plan = SECONDARY_N1 if world == 1 else SECONDARY_MULTI
+        for name, dtype in plan:
+            gc.collect()
+            torch.cuda.empty_cache()
+            elapsed = time.monotonic() - t_start
+            flag = torch.tensor([1.0 if elapsed > args.secondary_budget else 0.0], device=dev)
+            if world > 1:
+                dist.broadcast(flag, 0)  # every rank takes the same decision
+            if flag.item() > 0:
+                if rank == 0:
+                    sec[name] = {"skipped": f"time box: {elapsed:.0f} s elapsed > {args.secondary_budget:.0f} s"}
+                continue
+            a2 = copy.copy(args)
+            a2.dtype, a2.ring, a2.total_log2, a2.horizon_set = dtype, 0, 0, False
+            key = name[:-4] if name.endswith("_f64") else name
+            Wc = WORKLOADS[key]
+            k2 = max(3, min(K, 20 if Wc.use_graph else (3 if key == "c4_rollout" else 10)))
+            w2 = Wc(a2, rank, world, dev)
+            try:
+                rec = measure(w2, ctx, k2, 3, a2)
+            except Exception as e:  # a secondary must never cost the primary line
+                rec = {"error": f"{type(e).__name__}: {e}"[:300]}
+                if world > 1:
+                    raise
+            w2.teardown()
+            del w2
+            if rank == 0 and rec is not None:
+                sec[name] = {k: rec[k] for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "scaling", "dtype", "config", "roofline",
+                                                 "e2e", "gpu_launches", "clocks") if k in rec} if "error" not in rec else rec
+        if rank == 0:
+            line["secondary"] = sec
+    if rank == 0:
+        sampler.finish()
+        emit_json_line(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -992,7 +1332,13 @@ def main():
     ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS))
+    ap.add_argument("--dtype", default="f32", choices=["f32", "f64"], help="f64 = the float64 reference-exact mode (c1, c2, i2p, c3_*, c4)")
+    ap.add_argument("--launch", default="auto", choices=["auto", "graph", "stream"],
+                    help="launch-bound workloads (c1, c2, i2p): K steps as one CUDA graph (auto), or K step() calls queued behind a spinning kernel")
+    ap.add_argument("--presleep", type=int, default=-1, help="development knob: cycles of the spinning kernel queued before the timed region of launch-bound workloads (-1 = default)")
+    ap.add_argument("--no-secondary", action="store_true", help="default workload only: skip the `secondary` records of the other BASELINE configs")
+    ap.add_argument("--secondary-budget", type=float, default=240.0, help="seconds after which remaining secondary workloads are skipped")
     ap.add_argument("--ring", type=int, default=0)
     ap.add_argument("--e2e-steps", type=int, default=30)
     ap.add_argument("--no-cpu", action="store_true")
@@ -1002,6 +1348,9 @@ def main():
     args.horizon_set = args.horizon is not None
     if args.horizon is None:
         args.horizon = 100
+    args.secondary = args.workload is None and not args.no_secondary and args.impl == "ours" and args.dtype == "f32"
+    if args.workload is None:
+        args.workload = "c2"
     if args.steps is None:
         args.steps = 2000 if WORKLOADS[args.workload].use_graph else 20
         if args.impl == "reference":

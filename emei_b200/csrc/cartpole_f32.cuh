@@ -62,7 +62,7 @@ __device__ __forceinline__ float load_action_f32(const void* __restrict__ action
 //
 // integrate_fast: f32::cartpole_integrate (one sincos + angle addition).  Returns false when its guard trips
 // (|theta| > kSinCosSaneMax, a sub-step increment beyond pi/4, Inf): the caller then restores the state and calls
-// integrate_libm, which evaluates sincosf at every sub-step.  cos_cp = cos of the final cart-pole angle.
+// integrate_libm (same structure, range-reduced evaluations).  cos_cp = cos of the final cart-pole angle.
 template <bool IP, int FR>
 __device__ __forceinline__ bool integrate_fast(float4& y, float f_mt, uint32_t flip, const CartPoleF32Consts& k, float& cos_cp) {
   f32::LaneMax<float> dmax;
@@ -73,15 +73,32 @@ __device__ __forceinline__ bool integrate_fast(float4& y, float f_mt, uint32_t f
     cos_cp = f32::cartpole_integrate<float, FR>(y.x, y.z, y.y, y.w, -f_mt, flip, k.k, k.freq_rate, dmax);  // [x, theta, v, omega]
   return th0 <= f32::kSinCosSaneMax && dmax.m <= f32::kDeltaMax;
 }
+// The cold path of an env whose guard tripped (a sub-step increment beyond pi/4, i.e. |theta_dot| > 39 rad/s at
+// dt = 0.02, or an absurd / non-finite angle).  Same structure as the fast path -- ONE sincos of the stored angle,
+// then (sin, cos) ROTATED by each sub-step's increment -- with range-reduced evaluations: libm for theta_0 (any
+// magnitude, NaN, Inf), the reduced kernels (libm beyond 1e5) for the increments.  Re-evaluating sincosf of the
+// float32 theta at every sub-step instead (the first version of this path) re-rounds theta to float32 between
+// sub-steps: at theta = 400 rad that is 1.5e-5 rad per sub-step, which the accelerations (hundreds of rad/s^2 per
+// radian for a fast pole) turn into 1e-4 of velocity error per step -- 100 x the absolute envelope.  The rotation
+// tracks theta_0 + sum(d) like the reference's float64 angle does.  cos_cp = cos of the final cart-pole angle.
 template <bool IP, int FR>
-__device__ __noinline__ float4 integrate_libm(float4 y, float f_mt, uint32_t flip, const f32::CartPoleK k, int freq_rate) {
+__device__ __noinline__ float4 integrate_libm(float4 y, float f_mt, uint32_t flip, const f32::CartPoleK k, int freq_rate, float* cos_cp) {
   const int fr = FR > 0 ? FR : freq_rate;
+  float &x = y.x, &xd = IP ? y.z : y.y, &th = IP ? y.y : y.z, &w = y.w;
+  float s, c;
+  f32::sincos_libm(th, &s, &c);
+  s = f32::u2f(f32::f2u(s) ^ flip);
+  c = f32::u2f(f32::f2u(c) ^ flip);
   for (int sub = 0; sub < fr; ++sub) {
-    if constexpr (!IP)
-      f32::cartpole_substep<true>(y.x, y.y, y.z, y.w, f_mt, 0u, k);
-    else
-      f32::cartpole_substep<true>(y.x, y.z, y.y, y.w, f_mt, flip, k);
+    const float d = f32::vmul(w, k.dt);
+    f32::cartpole_euler<float>(x, xd, th, w, s, c, -f_mt, k);
+    float sd, cd;
+    f32::sincos_fast(d, &sd, &cd);
+    const float s_next = f32::vfma(s, cd, f32::vmul(c, sd));
+    c = f32::vfma(c, cd, f32::vneg(f32::vmul(s, sd)));
+    s = s_next;
   }
+  *cos_cp = c;
   return y;
 }
 
@@ -159,9 +176,9 @@ __device__ __forceinline__ void cartpole_step_one(float4& y, float f_mt, uint32_
   float c;
   const bool ok = integrate_fast<IP, FR>(y, f_mt, flip, k, c);
   if (!ok) {
-    y = integrate_libm<IP, FR>(y0, f_mt, flip, k.k, k.freq_rate);
+    y = integrate_libm<IP, FR>(y0, f_mt, flip, k.k, k.freq_rate, &c);
   }
-  cartpole_outcome<IP>(y, ok, IP ? f32::u2f(f32::f2u(c) ^ flip) : c, k, rew, notdone, obs);
+  cartpole_outcome<IP>(y, true, IP ? f32::u2f(f32::f2u(c) ^ flip) : c, k, rew, notdone, obs);
 }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }

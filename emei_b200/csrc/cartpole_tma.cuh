@@ -20,12 +20,12 @@
 
 namespace emei {
 
-constexpr int kTmaGroups = 4;                                 // consumer groups per CTA
-constexpr int kTmaConsumers = kTmaGroups * kBlock;            // 1024 threads: 8 warps per scheduler at <= 64 registers
-constexpr int kTmaThreads = kTmaConsumers;                    // thread 0 doubles as the TMA producer
+constexpr int kTmaGroups = 4;                                 // consumer groups per CTA of the shipped shape (template GROUPS)
+constexpr int kTmaThreads = kTmaGroups * kBlock;              // 1024 threads: 8 warps per scheduler at <= 64 registers; thread 0 doubles as the TMA producer
 constexpr uint32_t kChunk = 2 * kBlock;                       // envs per chunk
 constexpr int kTmaSmemBudget = 208 * 1024;                    // ring bytes (of 227 KB per SM)
 constexpr int kTmaMaxSlots = 24;
+constexpr uint32_t kChunkOutBytes = kChunk * 5;               // BULK: staged reward (4 B) + done (1 B) of a chunk
 
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -92,8 +92,28 @@ __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src
                : "memory");
 }
 
-template <bool IP, int AK, int FR, bool HAS_OBS>
-__global__ void __launch_bounds__(kTmaThreads, 1)
+// 1-D bulk copy shared -> global (TMA engine), bulk-group completion.  16-byte aligned, size % 16 == 0.
+__device__ __forceinline__ void tma_store_1d(void* gmem_dst, uint32_t smem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(smem_src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void sts128(uint32_t addr, const float4& v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void sts32(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
+__device__ __forceinline__ void sts8(uint32_t addr, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+
+// GROUPS consumer groups of 256 threads per CTA (4: one CTA fills an SM; 2: half an SM, so that the CTA of the NEXT
+// step kernel -- launched early by programmatic dependent launch -- can already be resident, initialised and
+// parked in griddepcontrol.wait while this one computes).  BULK: a warp stages its 64 envs' outputs in shared memory
+// (next state in place over the staged input rows, reward and done in a per-slot output area) and its lane 0 writes
+// them with three bulk copies shared -> global; only for launches that never recycle a slot (the host decides).
+// Chunk c = envs [512 c, 512 c + 512); warp w of a group owns the 64 contiguous envs 512 c + 64 w ..: lane l takes
+// 64 w + l and 64 w + 32 + l.
+template <bool IP, int AK, int FR, bool HAS_OBS, int GROUPS = kTmaGroups, bool BULK = false>
+__global__ void __launch_bounds__(GROUPS * kBlock, GROUPS == 4 ? 1 : 2)
     cartpole_step_f32_tma_kernel(const float4* state_in, float4* state_out, float4* obs_out,
                                  const void* __restrict__ action, float* __restrict__ reward, uint8_t* __restrict__ done,
                                  double* stats, uint32_t n, int n_slots, int action_via_tma, const CartPoleF32Consts k) {
@@ -103,7 +123,8 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
   // layout: [n_slots] state chunks (8 KB each) | [n_slots] action chunks | full[n_slots] | empty[n_slots] | reduction scratch
   float4* s_state = reinterpret_cast<float4*>(smem_raw);
   ActT* s_act = reinterpret_cast<ActT*>(smem_raw + static_cast<size_t>(n_slots) * kChunk * sizeof(float4));
-  uint64_t* full = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(s_act) + static_cast<size_t>(n_slots) * kChunk * sizeof(ActT));
+  unsigned char* s_out = reinterpret_cast<unsigned char*>(s_act) + static_cast<size_t>(n_slots) * kChunk * sizeof(ActT);  // BULK: [n_slots] x (512 rewards | 512 done bytes)
+  uint64_t* full = reinterpret_cast<uint64_t*>(s_out + (BULK ? static_cast<size_t>(n_slots) * kChunkOutBytes : 0));
   uint64_t* empty = full + n_slots;
   const uint32_t tid = threadIdx.x;
   const uint32_t n_chunks = (n + kChunk - 1) / kChunk;
@@ -139,12 +160,12 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
     // of the batch: no per-lane predicates) and the ragged tail.
     const uint32_t g = tid / kBlock, t = tid % kBlock;
     const uint32_t flip = ip_flip(IP, k.variant);
-    const uint32_t spg = static_cast<uint32_t>(n_slots) / kTmaGroups;                  // slots per group (n_slots % 4 == 0)
-    const uint32_t my_g = my_chunks > g ? (my_chunks - g + kTmaGroups - 1) / kTmaGroups : 0;  // this group's chunks
+    const uint32_t spg = static_cast<uint32_t>(n_slots) / GROUPS;                  // slots per group (n_slots % GROUPS == 0)
+    const uint32_t my_g = my_chunks > g ? (my_chunks - g + GROUPS - 1) / GROUPS : 0;  // this group's chunks
     const bool recycling = my_g > spg;  // group-uniform: the ring is reused
     const uint32_t slot0 = g * spg;
     auto issue = [&](uint32_t gg, uint32_t m, uint32_t sl) {  // chunk m of group gg into slot sl
-      const uint32_t c = blockIdx.x + (gg + m * kTmaGroups) * gridDim.x;
+      const uint32_t c = blockIdx.x + (gg + m * GROUPS) * gridDim.x;
       const uint32_t base = c * kChunk;
       const uint32_t cnt = n - base < kChunk ? n - base : kChunk;
       const bool act_tma = action_via_tma && cnt == kChunk;  // partial tail: consumers read their actions directly
@@ -159,32 +180,35 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
     // complete late (10.8 us per step at 2^20 envs instead of 9.7); issued in order, chunk 0 lands first.
     if (tid == 0) {
       const uint32_t first = my_chunks < static_cast<uint32_t>(n_slots) ? my_chunks : static_cast<uint32_t>(n_slots);
-      for (uint32_t j = 0; j < first; ++j) issue(j % kTmaGroups, j / kTmaGroups, (j % kTmaGroups) * spg + j / kTmaGroups);
+      for (uint32_t j = 0; j < first; ++j) issue(j % GROUPS, j / GROUPS, (j % GROUPS) * spg + j / GROUPS);
     }
     // 32-bit shared-window addresses (the generic-pointer forms re-derive the window base per chunk)
-    const uint32_t state_u32 = smem_u32(s_state) + t * 16u, full_u32 = smem_u32(full), empty_u32 = smem_u32(empty);
-    const uint32_t act_u32 = smem_u32(s_act) + t * static_cast<uint32_t>(sizeof(ActT));
-    const uint32_t i_step = kTmaGroups * gridDim.x * kChunk;
-    uint32_t i = (blockIdx.x + g * gridDim.x) * kChunk + t;  // env A of this thread in the current chunk; env B = i + kBlock
+    const uint32_t tw = (t >> 5) * 64u + (t & 31u);  // env A of this thread within a chunk; env B = tw + 32
+    const uint32_t state_u32 = smem_u32(s_state) + tw * 16u, full_u32 = smem_u32(full), empty_u32 = smem_u32(empty);
+    const uint32_t act_u32 = smem_u32(s_act) + tw * static_cast<uint32_t>(sizeof(ActT));
+    [[maybe_unused]] const uint32_t out_u32 = smem_u32(s_out);
+    const uint32_t i_step = GROUPS * gridDim.x * kChunk;
+    uint32_t i = (blockIdx.x + g * gridDim.x) * kChunk + tw;  // env A of this thread in the current chunk; env B = i + 32
     uint32_t slot = slot0, phase = 0u;                      // slot / parity of the chunk consumed now
     uint32_t prev_slot = slot0, prev_phase = 0u;            // ... and of the previous iteration (the one to refill)
 
     auto body = [&](auto full_tag) {
       constexpr bool FULL = decltype(full_tag)::value;
-      const bool live_a = FULL || i < n, live_b = FULL || i + kBlock < n;
+      constexpr uint32_t kB = 32u;  // env B = env A + 32
+      const bool live_a = FULL || i < n, live_b = FULL || i + kB < n;
       const bool act_tma = FULL && action_via_tma;  // partial tail: consumers read their actions directly
       mbar_wait_u32(full_u32 + slot * 8u, phase);
       const uint32_t sl = state_u32 + slot * (kChunk * 16u);
       float4 ya = live_a ? lds128(sl) : make_float4(0.f, 0.f, 0.f, 0.f);
-      float4 yb = live_b ? lds128(sl + kBlock * 16u) : make_float4(0.f, 0.f, 0.f, 0.f);
+      float4 yb = live_b ? lds128(sl + kB * 16u) : make_float4(0.f, 0.f, 0.f, 0.f);
       float aa = 0.f, ab = 0.f;
       if (act_tma) {
         const uint32_t al = act_u32 + slot * (kChunk * static_cast<uint32_t>(sizeof(ActT)));
         aa = static_cast<float>(lds_as<ActT>(al));
-        ab = static_cast<float>(lds_as<ActT>(al + kBlock * static_cast<uint32_t>(sizeof(ActT))));
+        ab = static_cast<float>(lds_as<ActT>(al + kB * static_cast<uint32_t>(sizeof(ActT))));
       } else {
         if (live_a) aa = static_cast<float>(__ldg(act + i));
-        if (live_b) ab = static_cast<float>(__ldg(act + i + kBlock));
+        if (live_b) ab = static_cast<float>(__ldg(act + i + kB));
       }
       if (recycling) {
         __syncwarp();
@@ -227,32 +251,65 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
       const bool ok_a = th0a <= f32::kSinCosSaneMax && dmax.a <= f32::kDeltaMax;
       const bool ok_b = th0b <= f32::kSinCosSaneMax && dmax.b <= f32::kDeltaMax;
       if (!(ok_a && ok_b)) {
-        if (!ok_a && live_a) na = integrate_libm<IP, FR>(state_in[i], fa, flip, k.k, k.freq_rate);
-        if (!ok_b && live_b) nb = integrate_libm<IP, FR>(state_in[i + kBlock], fb, flip, k.k, k.freq_rate);
+        if (!ok_a && live_a) {
+          na = integrate_libm<IP, FR>(state_in[i], fa, flip, k.k, k.freq_rate, &ca);
+          if constexpr (IP) ca = f32::u2f(f32::f2u(ca) ^ flip);
+        }
+        if (!ok_b && live_b) {
+          nb = integrate_libm<IP, FR>(state_in[i + kB], fb, flip, k.k, k.freq_rate, &cb);
+          if constexpr (IP) cb = f32::u2f(f32::f2u(cb) ^ flip);
+        }
       }
       float rew_a, rew_b;
       bool nd_a, nd_b;
       float4 oa, ob;
-      cartpole_outcome<IP>(na, ok_a, ca, k, rew_a, nd_a, oa);
-      cartpole_outcome<IP>(nb, ok_b, cb, k, rew_b, nd_b, ob);
-      float4* so = state_out + i;
-      float* ro = reward + i;
-      uint8_t* dn = done + i;
-      if (live_a) {
-        so[0] = na;
-        if constexpr (HAS_OBS) obs_out[i] = oa;
-        ro[0] = rew_a;
-        dn[0] = nd_a ? 0 : 1;
-        r_acc += rew_a;
-        d_cnt += nd_a ? 0u : 1u;
-      }
-      if (live_b) {
-        so[kBlock] = nb;
-        if constexpr (HAS_OBS) obs_out[i + kBlock] = ob;
-        ro[kBlock] = rew_b;
-        dn[kBlock] = nd_b ? 0 : 1;
-        r_acc += rew_b;
-        d_cnt += nd_b ? 0u : 1u;
+      cartpole_outcome<IP>(na, true, ca, k, rew_a, nd_a, oa);
+      cartpole_outcome<IP>(nb, true, cb, k, rew_b, nd_b, ob);
+      if constexpr (BULK && FULL) {
+        // stage the outputs: next state over this thread's own input rows, reward / done in the slot's output area;
+        // lane 0 then writes the warp's 64 envs with three bulk copies (1024 + 256 + 64 bytes)
+        const uint32_t ol = out_u32 + slot * kChunkOutBytes;
+        sts128(sl, na);
+        sts128(sl + kB * 16u, nb);
+        sts32(ol + tw * 4u, rew_a);
+        sts32(ol + (tw + kB) * 4u, rew_b);
+        sts8(ol + kChunk * 4u + tw, nd_a ? 0u : 1u);
+        sts8(ol + kChunk * 4u + tw + kB, nd_b ? 0u : 1u);
+        if constexpr (HAS_OBS) {
+          obs_out[i] = oa;
+          obs_out[i + kB] = ob;
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if ((t & 31u) == 0) {
+          const uint32_t w0 = tw;  // first env of this warp within the chunk
+          tma_store_1d(state_out + i, sl, 64u * 16u);
+          tma_store_1d(reward + i, ol + w0 * 4u, 64u * 4u);
+          tma_store_1d(done + i, ol + kChunk * 4u + w0, 64u);
+          tma_store_commit();
+        }
+        r_acc += rew_a + rew_b;
+        d_cnt += (nd_a ? 0u : 1u) + (nd_b ? 0u : 1u);
+      } else {
+        float4* so = state_out + i;
+        float* ro = reward + i;
+        uint8_t* dn = done + i;
+        if (live_a) {
+          so[0] = na;
+          if constexpr (HAS_OBS) obs_out[i] = oa;
+          ro[0] = rew_a;
+          dn[0] = nd_a ? 0 : 1;
+          r_acc += rew_a;
+          d_cnt += nd_a ? 0u : 1u;
+        }
+        if (live_b) {
+          so[kB] = nb;
+          if constexpr (HAS_OBS) obs_out[i + kB] = ob;
+          ro[kB] = rew_b;
+          dn[kB] = nd_b ? 0 : 1;
+          r_acc += rew_b;
+          d_cnt += nd_b ? 0u : 1u;
+        }
       }
     };
 
@@ -261,7 +318,7 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
         mbar_wait(&empty[prev_slot], prev_phase);
         issue(g, m - 1 + spg, prev_slot);
       }
-      if (i - t + kChunk <= n)
+      if (i - tw + kChunk <= n)
         body(std::true_type{});
       else
         body(std::false_type{});
@@ -274,7 +331,11 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
       }
     }
   }
+  if constexpr (BULK) {  // the staged outputs must have been read before the CTA's shared memory goes away
+    if ((tid & 31u) == 0) tma_store_wait_read0();
+  }
   // ---- statistics: warp shuffles -> shared -> one atomic pair per CTA
+  constexpr int kTmaThreads = GROUPS * kBlock;
   if (stats != nullptr) {  // uniform across the grid
     double* s_r = reinterpret_cast<double*>(empty + n_slots);
     unsigned* s_d = reinterpret_cast<unsigned*>(s_r + kTmaThreads / 32);
@@ -331,16 +392,17 @@ __global__ void __launch_bounds__(kSmallBlock)
 }
 
 // slots, dynamic shared memory bytes for an action element size
-inline void tma_ring_shape(int action_bytes, int64_t chunks_per_cta, int* n_slots, size_t* smem_bytes) {
-  const int slot_bytes = static_cast<int>(kChunk) * (16 + action_bytes);
-  int s = kTmaSmemBudget / slot_bytes;
+inline void tma_ring_shape(int action_bytes, int64_t chunks_per_cta, int* n_slots, size_t* smem_bytes, int groups = kTmaGroups,
+                           bool bulk = false, int budget = kTmaSmemBudget) {
+  const int slot_bytes = static_cast<int>(kChunk) * (16 + action_bytes) + (bulk ? static_cast<int>(kChunkOutBytes) : 0);
+  int s = budget / slot_bytes;
   if (s > kTmaMaxSlots) s = kTmaMaxSlots;
   if (s > chunks_per_cta) s = static_cast<int>(chunks_per_cta);
-  s = (s + kTmaGroups - 1) / kTmaGroups * kTmaGroups;  // every consumer group owns n_slots / kTmaGroups slots
-  while (s * slot_bytes > kTmaSmemBudget) s -= kTmaGroups;
-  if (s < kTmaGroups) s = kTmaGroups;
+  s = (s + groups - 1) / groups * groups;  // every consumer group owns n_slots / groups slots
+  while (s * slot_bytes > budget) s -= groups;
+  if (s < groups) s = groups;
   *n_slots = s;
-  *smem_bytes = static_cast<size_t>(s) * slot_bytes + 2 * s * sizeof(uint64_t) + (kTmaThreads / 32) * (sizeof(double) + sizeof(unsigned)) + 16;
+  *smem_bytes = static_cast<size_t>(s) * slot_bytes + 2 * s * sizeof(uint64_t) + (groups * kBlock / 32) * (sizeof(double) + sizeof(unsigned)) + 16;
 }
 
 // opt in to > 48 KB of dynamic shared memory: the attribute is PER DEVICE, so it is set once per (kernel

@@ -17,6 +17,7 @@ namespace emei {
 
 struct ChargedBallF32Consts {
   float mg /* m*g */, inv_mr /* 1/(m*r) */, m_r /* m*r */, inv_m, g, r, inv_r, charge, h, land_thr, eps;
+  float r2m1 /* r*r - 1 */, two_eps_r /* 2*eps*r */;
   int freq_rate;
 };
 
@@ -33,6 +34,8 @@ inline ChargedBallF32Consts make_cb_f32_consts(const emei_charged_ball_params& p
   k.h = static_cast<float>(p.time_step / p.freq_rate);  // charged_ball.py:58,63
   k.land_thr = static_cast<float>(p.radius * p.radius + 0.001);  // :64
   k.eps = 1e-8f;
+  k.r2m1 = static_cast<float>(p.radius * p.radius - 1.0);
+  k.two_eps_r = static_cast<float>(2.0 * 1e-8 * p.radius);
   k.freq_rate = p.freq_rate;
   return k;
 }
@@ -43,17 +46,37 @@ __device__ __forceinline__ float sqrt_fast(float x) {  // sqrt.approx: max relat
   return r;
 }
 
+// atan2(x, c) for c >= 0 (result in [-pi/2, pi/2]): octant reduction to |z| <= tan(pi/8) with ONE MUFU.RCP, then the
+// classic single-precision minimax polynomial atan z = z + z^3 P(z^2) (|error| <= 1e-7 there).
+__device__ __forceinline__ float cb_atan2_pos(float x, float c) {
+  const float ax = fabsf(x);
+  const float hi = fmaxf(ax, c), lo = fminf(ax, c);
+  const bool mid = lo > 0.41421356237309503f * hi;  // atan(lo / hi) = pi/4 + atan((lo - hi) / (lo + hi))
+  const float num = mid ? lo - hi : lo, den = mid ? lo + hi : hi;
+  const float z = num * f32::rcp_fast(den), z2 = z * z;
+  float pz = fmaf(8.05374449538e-2f, z2, -1.38776856032e-1f);
+  pz = fmaf(pz, z2, 1.99777106478e-1f);
+  pz = fmaf(pz, z2, -3.33329491539e-1f);
+  float a = fmaf(pz * z2, z, z) + (mid ? 0.78539816339744830962f : 0.0f);
+  a = ax > c ? 1.57079632679489661923f - a : a;  // the octant swap
+  return copysignf(a, x);
+}
+
 // charged_ball.py:30-36, evaluated only when a ball lands (2 % of env-steps, but 43 % of warp-steps in a
-// rollout, so its length matters: MUFU sqrt / reciprocal instead of the IEEE sequences, and the `% 2 pi` of an
-// angle that is already in [-pi/2, 3pi/2] as one select -- the same bits as fmodf there).  The MUFU results
-// are within 1 ulp each, so the asin argument may exceed 1 by an ulp or two where the IEEE quotient cannot:
-// clamped (NaN stays NaN).
-__device__ __forceinline__ float cb_get_angle_f32(float x, float y, float r, float eps) {
+// rollout, so its length matters).  The reference computes  a = asin(x / (scale * r + 1e-8)).  Evaluating asin of
+// a float32 quotient loses half the digits where |x| -> scale (the derivative 1 / sqrt(1 - arg^2) is unbounded), so
+// the float32 path uses the identity asin(q) = atan2(q, sqrt(1 - q^2)) with the complement formed WITHOUT
+// cancellation: for q = x / D, D = scale * r + eps,
+//     D^2 - x^2 = y^2 + scale^2 (r^2 - 1) + 2 eps r scale + eps^2
+// (the eps term is what keeps the reference's angle 1.4e-4 rad away from +-pi/2 at y = 0: it is kept).
+// Well conditioned everywhere: the landing angle meets the 1e-5 / 1e-6 envelope for every landing position.
+// `% 2 pi` of an angle that is already in [-pi/2, 3 pi/2] is one select -- the same bits as fmodf there.
+__device__ __forceinline__ float cb_get_angle_f32(float x, float y, float r, float eps, float r2m1, float two_eps_r) {
   const float scale = sqrt_fast(fmaf(x, x, y * y));
-  float arg = x * f32::rcp_fast(fmaf(scale, r, eps));
-  arg = fabsf(arg) > 1.0f ? copysignf(1.0f, arg) : arg;
-  const float a = asinf(arg);
+  const float c2 = fmaf(y, y, fmaf(scale * scale, r2m1, two_eps_r * scale));  // D^2 - x^2 >= 0 for r >= 1
+  const float a = cb_atan2_pos(x, sqrt_fast(fmaxf(c2, 0.0f)));
   const float angle = (y > 0.f) ? a : (3.14159265358979323846f - a);
+  (void)eps;
   return angle < 0.f ? angle + 6.28318530717958647692f : angle + 0.0f;  // python `%`: result in [0, 2 pi), +0
 }
 
@@ -117,7 +140,7 @@ __device__ __forceinline__ float cb_env_step(CBRegs& e, float E, const ChargedBa
       f.y = ny;
       if (fmaf(f.x, f.x, f.y * f.y) > k.land_thr) {
         on = true;
-        theta = cb_get_angle_f32(f.x, f.y, k.r, k.eps);
+        theta = cb_get_angle_f32(f.x, f.y, k.r, k.eps, k.r2m1, k.two_eps_r);
         // _angle_greater(_get_angle(vx, vy), theta) (:38-42,48-51) asks whether the velocity direction is ahead
         // of the position direction on the circle of angles, i.e. sin(v_angle - theta) > 0, i.e. the sign of
         // the cross product vx*y - vy*x: same answer as comparing the two angles (wrap rule included) except

@@ -166,12 +166,18 @@ struct CartPoleDyn {
     const bool ok_a = th0a <= f32::kSinCosSaneMax && dmax.a <= f32::kDeltaMax;
     const bool ok_b = th0b <= f32::kSinCosSaneMax && dmax.b <= f32::kDeltaMax;
     if (!(ok_a && ok_b)) {  // cold: the integrator's guard tripped (f32math.cuh)
-      if (!ok_a) na = integrate_libm<IP, FR>(ya, fa, flip, k.k, k.freq_rate);
-      if (!ok_b) nb = integrate_libm<IP, FR>(yb, fb, flip, k.k, k.freq_rate);
+      if (!ok_a) {
+        na = integrate_libm<IP, FR>(ya, fa, flip, k.k, k.freq_rate, &ca);
+        if constexpr (IP) ca = f32::u2f(f32::f2u(ca) ^ flip);
+      }
+      if (!ok_b) {
+        nb = integrate_libm<IP, FR>(yb, fb, flip, k.k, k.freq_rate, &cb);
+        if constexpr (IP) cb = f32::u2f(f32::f2u(cb) ^ flip);
+      }
     }
     bool nd_a, nd_b;
-    cartpole_outcome<IP>(na, ok_a, ca, k, rew[0], nd_a, next_obs[0]);
-    cartpole_outcome<IP>(nb, ok_b, cb, k, rew[1], nd_b, next_obs[1]);
+    cartpole_outcome<IP>(na, true, ca, k, rew[0], nd_a, next_obs[0]);
+    cartpole_outcome<IP>(nb, true, cb, k, rew[1], nd_b, next_obs[1]);
     e[0].y = na;
     e[1].y = nb;
     terminated[0] = !nd_a;

@@ -474,19 +474,20 @@ def score(env, params: _lib.ScoringParams, obs, pre_obs=None, action=None, want=
         if tuple(p.shape) != tuple(o.shape) or a.shape[0] != b:
             raise ValueError("obs / pre_obs / action batch shapes disagree")
     # ---- the other half of a reward / terminal pair asked for on the same tensors: reuse the fused pass
+    # Only the COMPLEMENTARY half is ever served (reward after terminal, terminal after reward), once: repeating the
+    # same call, or get_batch_reward_terminal, always runs the kernels.
     key = key_obs = None
-    if not was_np:
+    if not was_np and want in ("reward", "terminal"):
         key_obs = _score_cache_key(env, params, (o,), group)
-        hit = getattr(env, "_score_cache", None)
-        if hit is not None and hit[2] == _lib.launch_count:
-            if not needs_pre or p is not None:
-                key = _score_cache_key(env, params, (o, p, a), group)
-                if hit[0] == key:
-                    return hit[3], hit[4], was_np
-            elif hit[1] == key_obs:  # terminal asked for with obs alone: the flags depend on obs only
-                return None, hit[4], was_np
-        if key is None and (not needs_pre or p is not None):
+        if not needs_pre or p is not None:
             key = _score_cache_key(env, params, (o, p, a), group)
+        hit = getattr(env, "_score_cache", None)
+        env._score_cache = None
+        if hit is not None and hit[2] == _lib.launch_count and hit[5] != want:
+            if key is not None and hit[0] == key:
+                return hit[3], hit[4], was_np
+            if key is None and want == "terminal" and hit[1] == key_obs:  # terminal with obs alone: the flags depend on obs only
+                return None, hit[4], was_np
     sumsq = None
     if needs_pre and p is not None:
         sumsq = _sumsq(env, _aligned16(a), group)
@@ -507,7 +508,7 @@ def score(env, params: _lib.ScoringParams, obs, pre_obs=None, action=None, want=
     )
     done = done.view(torch.bool)
     if key is not None and not getattr(env, "accumulate_scoring_stats", False):
-        env._score_cache = (key, key_obs, _lib.launch_count, reward, done)
+        env._score_cache = (key, key_obs, _lib.launch_count, reward, done, want)
     return reward, done, was_np
 
 

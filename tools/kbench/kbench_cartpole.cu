@@ -6,7 +6,6 @@
 #include <cstdlib>
 #include <vector>
 #include "../../emei_b200/csrc/cartpole_tma.cuh"
-#include "cartpole_tma_prev.cuh"
 
 using namespace emei;
 #include <cstring>
@@ -112,7 +111,65 @@ float time_graph(F launch, int K, cudaStream_t s, int reps = 5) {
   return best * 1e3f / K;  // us per launch
 }
 
-template <int FR, bool PREV = false>
+__global__ void spin_kernel(long long cycles) {
+  const long long t0 = clock64();
+  while (clock64() - t0 < cycles) {
+  }
+}
+
+// K plain stream launches queued behind a spinning kernel (no graph): what a caller of step() in a loop gets
+template <typename F>
+float time_stream(F launch, int K, cudaStream_t s, int reps = 5) {
+  for (int i = 0; i < 8; ++i) launch(i);
+  CK(cudaStreamSynchronize(s));
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  float best = 1e30f;
+  for (int r = 0; r < reps; ++r) {
+    spin_kernel<<<1, 1, 0, s>>>(400000 + 30000ll * K);
+    CK(cudaEventRecord(e0, s));
+    for (int i = 0; i < K; ++i) launch(i);
+    CK(cudaEventRecord(e1, s)); CK(cudaStreamSynchronize(s));
+    float ms; cudaEventElapsedTime(&ms, e0, e1); if (ms < best) best = ms;
+  }
+  return best * 1e3f / K;
+}
+
+// shape variants of the shipped kernel: GROUPS consumer groups per CTA, BULK stores, CTAs per SM, ring budget
+template <int GROUPS, bool BULK>
+void run_tma2(const char* name, Ring& R, uint32_t n, int K, cudaStream_t s, int ctas_per_sm, int budget_kb) {
+  SKIP(name);
+  emei_cartpole_params p = {};
+  p.gravity = 9.8; p.mass_pole = 0.1; p.total_mass = 1.1; p.length = 0.5; p.pole_mass_length = 0.05; p.force_mag = 10.0;
+  p.x_threshold = 5.0; p.theta_threshold = 0.2; p.dt = 0.02; p.freq_rate = 4; p.variant = EMEI_CARTPOLE_SWINGUP;
+  p.action_kind = EMEI_ACTION_CONTINUOUS_F32;
+  CartPoleF32Consts k = make_cartpole_f32_consts(p);
+  const int64_t chunks = (n + kChunk - 1) / kChunk;
+  const int64_t cap = (int64_t)kNumSMs * ctas_per_sm;
+  const int grid = (int)(chunks < cap ? chunks : cap);
+  int n_slots; size_t smem;
+  tma_ring_shape(4, (chunks + grid - 1) / grid, &n_slots, &smem, GROUPS, BULK, budget_kb * 1024);
+  const bool recycles = (chunks + grid - 1) / grid > n_slots;
+  if (BULK && recycles) { printf("%-52s skipped: BULK needs a ring that holds the CTA's whole share\n", name); return; }
+  double* stats; CK(cudaMalloc(&stats, 16)); CK(cudaMemset(stats, 0, 16));
+  const int ring = (int)R.in.size();
+  auto kern = cartpole_step_f32_tma_kernel<false, EMEI_ACTION_CONTINUOUS_F32, 4, false, GROUPS, BULK>;
+  CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  auto launch = [&](int i) {
+    int j = i % ring;
+    launch_pdl_smem(kern, grid, GROUPS * kBlock, smem, s, (const float4*)R.in[j], (float4*)R.out[j], (float4*)nullptr, (const void*)R.act[j], R.rew[j], R.done[j], stats, n, n_slots, 1, k);
+  };
+  float us = time_graph(launch, K, s);
+  CK(cudaGetLastError());
+  float us20g = time_graph(launch, 20, s, 9);
+  float us20s = time_stream(launch, 20, s, 9);
+  CK(cudaGetLastError());
+  int occ = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, GROUPS * kBlock, smem);
+  printf("%-52s grid=%4d thr=%4d slots=%2d smem=%6zu occ=%d  graph K=%d: %6.2f us  %5.0f GB/s | K=20 graph %6.2f us, K=20 stream launches %6.2f us\n",
+         name, grid, GROUPS * kBlock, n_slots, smem, occ, K, us, 41.0 * n / us * 1e-3, us20g, us20s);
+  cudaFree(stats);
+}
+
+template <int FR>
 void run_tma(const char* name, Ring& R, uint32_t n, int K, cudaStream_t s, int slots_cap = 0) {
   SKIP(name);
   emei_cartpole_params p = {};
@@ -127,8 +184,7 @@ void run_tma(const char* name, Ring& R, uint32_t n, int K, cudaStream_t s, int s
   if (slots_cap && n_slots > slots_cap) { n_slots = slots_cap; smem = (size_t)n_slots * kChunk * 20 + 2 * n_slots * 8 + (kTmaThreads / 32) * 12 + 16; }
   double* stats; CK(cudaMalloc(&stats, 16)); CK(cudaMemset(stats, 0, 16));
   const int ring = (int)R.in.size();
-  auto kern = PREV ? cartpole_step_f32_tma_prev_kernel<false, EMEI_ACTION_CONTINUOUS_F32, FR, false>
-                   : cartpole_step_f32_tma_kernel<false, EMEI_ACTION_CONTINUOUS_F32, FR, false>;
+  auto kern = cartpole_step_f32_tma_kernel<false, EMEI_ACTION_CONTINUOUS_F32, FR, false>;
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   auto launch = [&](int i) {
     int j = i % ring;
@@ -208,9 +264,15 @@ int main(int argc, char** argv) {
   run_compute<4, 4, false>("compute-only scalar fr4 minb4 angle-addition", R, n, K, s);
   run_compute2<4, 4, true>("compute-only packed fr4 minb4 sincos/sub-step", R, n, K, s);
   run_compute2<4, 4, false>("compute-only packed fr4 minb4 angle-addition", R, n, K, s);
-  run_tma<4, true>("TMA packed fr4, previous loop structure", R, n, K, s);
   run_tma<4>("TMA packed fr4 (shipped)", R, n, K, s);
   run_tma<4>("TMA packed fr4 slots<=8", R, n, K, s, 8);
+  // ---- round 2: shape variants (GROUPS per CTA, bulk stores, CTAs per SM, ring budget in KB)
+  run_tma2<4, false>("r2 G4 direct stores (shipped shape)", R, n, K, s, 1, 208);
+  run_tma2<4, true>("r2 G4 BULK stores", R, n, K, s, 1, 216);
+  run_tma2<2, false>("r2 G2 half-SM, 1 CTA/SM/kernel, 10 slots", R, n, K, s, 1, 104);
+  run_tma2<2, false>("r2 G2 half-SM, 1 CTA/SM/kernel, 8 slots", R, n, K, s, 1, 84);
+  run_tma2<2, false>("r2 G2 2 CTAs/SM, 7 slots each", R, n, K, s, 2, 104);
+  run_tma2<2, true>("r2 G2 2 CTAs/SM, 7 slots each, BULK", R, n, K, s, 2, 108);
   run_tma<0>("TMA packed fr-runtime", R, n, K, s);
   run_tma<1>("TMA packed fr1", R, n, K, s);
   return 0;
