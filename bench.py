@@ -262,7 +262,7 @@ class Workload:
     kernel = kernel_f64 = ""
     # algorithmic math per unit: FP operations (an add, a multiply, an FMA or a divide is ONE op) and
     # special-function evaluations (sin, cos, rcp/div, sqrt, asin: one MUFU-class op each); None = trivial / not stated
-    alg_fp_ops = alg_sfu_ops = None
+    alg_fp_ops = alg_sfu_ops = alg_fp64_ops = None
     inst_per_unit = None  # thread-level SASS instructions per unit from ncu (issue utilisation, reported beside the roofline)
     cpu_kind = None  # which oracle routine is the CPU baseline
     cpu_sample = 1 << 20
@@ -325,6 +325,7 @@ class CartPoleStep(Workload):
     # cartpole.py:48-60 per sub-step: 26 FP ops of which 4 divides, 1 sin + 1 cos; + reward cos and 2 ops, terminal 2 ops
     alg_fp_ops = 4 * 26 + 4
     alg_sfu_ops = 4 * (2 + 4) + 1
+    alg_fp64_ops = 4 * (22 + 4 * 10 + 2 * 20) + 20 + 4  # float64: 22 plain ops + 4 divides + sin + cos per sub-step; reward cos
     cpu_kind = "c2"
     supports_f64 = True
     inst_per_unit = 179.1  # 32 x smsp__inst_executed / envs, packed f32x2 (ncu, profiles/r01_launches_bench_c2.csv)
@@ -395,6 +396,7 @@ class IPStep(CartPoleStep):
     alg_bytes = 57  # state 16 + action 4 + next state 16 + wrapped obs 16 + reward 4 + done 1
     alg_bytes_f64 = 109
     alg_fp_ops, alg_sfu_ops = 26 + 4 + 3, (2 + 4) + 1
+    alg_fp64_ops = (22 + 4 * 10 + 2 * 20) + 20 + 4 + 10  # + the observation's floored modulo
     cpu_kind, cpu_sample = "c1", 1 << 20
     inst_per_unit = 202.5  # one env per thread, 128-thread CTAs: profiles/r01_launches_bench_c1.csv
 
@@ -602,6 +604,7 @@ class ChargedBall(Workload):
     # charged_ball.py:68-82 on the ring: sin, cos of theta before and after the update (4), 1 divide, ~20 FP ops;
     # reward: 1 sqrt + 1 divide (:158-160)
     alg_fp_ops, alg_sfu_ops = 22, 4 + 1 + 2
+    alg_fp64_ops = 20 + 4 * 20 + 10 + 2 * 10
     cpu_kind, cpu_sample = "c4", 1 << 20
     supports_f64 = True
 
@@ -1030,11 +1033,13 @@ def math_model(wl, units, seconds, sm_mhz, peak_gbs):
     clock = sm_mhz * 1e6
     if wl.f64:
         fp_peak = float(mp.get("fp64_tflops", 37.0)) * 1e12 / 2.0  # FMA-class FP64 operations per second
-        # a float64 sin or cos is ~60 FMA-class operations (CUDA libm, Payne-Hanek aside); divides / sqrt ~10
-        fp_ops = wl.alg_fp_ops + 60.0 * (wl.alg_sfu_ops or 0)
+        # float64 has no special-function unit: a divide or square root is ~10 FMA-class operations (Newton iterations),
+        # a sin or cos ~20 (reduction + a degree-13 polynomial); the kernel's SASS holds 142 FP64 instructions per
+        # sub-step iteration + epilogue, ~440 executed per C2 env-step, against 432 by this count
+        fp_ops = wl.alg_fp64_ops if wl.alg_fp64_ops is not None else wl.alg_fp_ops + 15.0 * (wl.alg_sfu_ops or 0)
         t_fp, t_sfu = fp_ops * units / fp_peak, 0.0
         peaks = {"fp64_ops_per_s": fp_peak, "source": "profiles/math_peaks.json fp64_tflops / 2 (tools/f2bench on the B200 box)",
-                 "fp64_ops_per_unit": fp_ops, "note": "special functions counted as 60 FP64 operations each (libm-grade evaluation)"}
+                 "fp64_ops_per_unit": fp_ops, "note": "plain FP ops + 10 per divide / sqrt + 20 per sin / cos (no FP64 special-function unit)"}
     else:
         fp_peak, sfu_peak = 148 * 128 * clock, 148 * 16 * clock
         t_fp, t_sfu = wl.alg_fp_ops * units / fp_peak, (wl.alg_sfu_ops or 0) * units / sfu_peak

@@ -132,6 +132,10 @@ _PROTOTYPES = {
     "emei_i2p_step": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int64, POINTER(I2PParams), _P]),
     "emei_ip_step_noisy": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int64, POINTER(CartPoleParams), POINTER(NoiseParams), _P]),
     "emei_i2p_step_noisy": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int64, POINTER(I2PParams), POINTER(NoiseParams), _P]),
+    "emei_cartpole_rollout_ref": (c_int, [_P] * 12 + [c_int64, POINTER(CartPoleParams), POINTER(RolloutParams), POINTER(NoiseParams), _P]),
+    "emei_i2p_rollout": (c_int, [_P] * 12 + [c_int64, POINTER(I2PParams), POINTER(RolloutParams), POINTER(c_double), POINTER(c_double),
+                                  POINTER(NoiseParams), _P]),
+    "emei_charged_ball_rollout_ref": (c_int, [_P] * 14 + [c_int64, POINTER(ChargedBallParams), POINTER(RolloutParams), _P]),
     "emei_reward_terminal": (c_int, [_P, _P, _P, _P, _P, _P, c_int64, POINTER(ScoringParams), _P]),
     "emei_reward_terminal_seq": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int64, POINTER(ScoringParams), _P]),
     "emei_sumsq": (c_int, [_P, c_int64, _P, _P, _P]),

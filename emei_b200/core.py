@@ -214,8 +214,6 @@ class EmeiEnv(Freezable):
         Returns a dict with those records (if any) and ``stats``: device double[6] = [sum of rewards,
         #terminated, #truncated, #episodes finished, sum of finished returns, sum of finished lengths];
         ``rollout_info(stats)`` turns it into the reference's avg_reward / avg_length / total_episode_num."""
-        if getattr(self, "_obs_noise_on", lambda: False)():
-            raise NotImplementedError("obs_noise_params != 0 is implemented for step() only (emei_ip_step_noisy / emei_i2p_step_noisy)")
         eng = getattr(self, "_ensure_engine", lambda: self._engine)()
         if eng is None or not hasattr(eng, "rollout"):
             raise NotImplementedError(f"{type(self).__name__} has no fused rollout kernel")
@@ -256,7 +254,9 @@ class EmeiEnv(Freezable):
                     ok = bool(((a >= 0) & (a < self.action_space.n)).all())
                 assert ok, "teacher-forced actions outside the action space"
         stats = torch.zeros(6, dtype=torch.float64, device=self.device)
-        out = eng.rollout(rp, a, bool(record), stats)
+        # obs_noise_params (mujoco_env.py:98-104): the step counter of the noise stream continues through the rollout
+        noise = getattr(self, "_next_obs_noise", lambda advance=1: None)(advance=int(horizon))
+        out = eng.rollout(rp, a, bool(record), stats, noise=noise)
         out["stats"] = stats
         return out
 
@@ -272,20 +272,21 @@ class EmeiEnv(Freezable):
         raise NotImplementedError(f"{type(self).__name__} has no fused rollout kernel")
 
     # ------------------------------------------------------------------ host-side callers
-    def step_host(self, action):
+    def step_host(self, action, outputs=None):
         """``step`` for callers that live on the host (the reference's numpy world): ``action`` is a
         numpy array / CPU tensor; returns numpy ``(obs, reward, terminated, False, {})``.
 
         Per call: pinned H2D copy of the actions, the step kernel, D2H copies of obs / reward / done
         into pinned staging buffers, one stream synchronise.  The returned arrays are views of those
-        staging buffers (valid until the next ``step_host``)."""
+        staging buffers (valid until the next ``step_host``).  ``outputs``: subset of ("obs", "reward", "done") to
+        download (default all, the reference's contract); the rest stays on the device and comes back as None."""
         from .engine import HostStaging
 
         if getattr(self, "_obs_noise_on", lambda: False)() and not hasattr(self._engine, "step_range"):
             raise NotImplementedError("obs_noise_params != 0 with step_host: inverted pendulum only (emei_ip_step_noisy)")
         if getattr(self, "_staging", None) is None:
             self._staging = HostStaging(self)
-        return self._staging.step(action)
+        return self._staging.step(action, outputs)
 
     # ------------------------------------------------------------------ seeding (gym.Env.reset(seed=))
     def _reseed(self, seed):

@@ -115,13 +115,85 @@ __device__ __forceinline__ R i2p_div(R a, R b) {
     return a / b;
 }
 
+// One env step on registers (shared by the step kernel and the rollout kernel of rollout_ref.cuh: same bits):
+// dynamics + optional state noise, the observation o and the variant's reward / not-done flag on it.
+template <typename R>
+__device__ __forceinline__ void i2p_env_step(R (&y)[6], R ctrl, const I2PConsts<R>& k, const NoiseConsts& z, unsigned long long env,
+                                             unsigned long long substep0, R (&o)[6], R& rew, bool& notdone) {
+  const R sign = k.swingup ? R(-1) : R(1);
+  ctrl = ctrl < k.ctrl_low ? k.ctrl_low : (ctrl > k.ctrl_high ? k.ctrl_high : ctrl);  // mj_step clamps ctrl
+  const R F = k.gear * ctrl;
+  for (int sub = 0; sub < k.freq_rate; ++sub) {
+    const R th0 = y[1], th1 = y[2], w0 = y[4], w1 = y[5];
+    R s0, c0, s1, c1, s01, c01;
+    i2p_sincos3<R>(th0, th1, s0, c0, s1, c1, s01, c01);
+    s0 = sign * s0, c0 = sign * c0, s01 = sign * s01, c01 = sign * c01;
+    const R a01 = k.k_a * c0 + k.k_b * c01;
+    const R a02 = k.k_b * c01;
+    const R a11 = k.k_e + R(2) * k.k_c * c1;
+    const R a12 = k.k_c * c1 + k.k_d;
+    const R a22 = k.k_d;
+    const R ws = w0 + w1;
+    const R b0 = F + k.k_a * s0 * (w0 * w0) + k.k_b * s01 * (ws * ws);
+    const R b1 = k.k_g1 * s0 + k.g * k.k_b * s01 + k.k_c * s1 * (w1 * (R(2) * w0 + w1));
+    const R b2 = k.k_b * (k.g * s01 - R(2) * k.l0 * s1 * (w0 * w0));
+    const R l10 = i2p_div(a01, k.a00);
+    const R l20 = i2p_div(a02, k.a00);
+    const R d1 = a11 - l10 * a01;
+    const R t12 = a12 - l10 * a02;
+    const R l21 = i2p_div(t12, d1);
+    const R d2 = a22 - l20 * a02 - l21 * t12;
+    const R y1 = b1 - l10 * b0;
+    const R y2 = b2 - l20 * b0 - l21 * y1;
+    const R z2 = i2p_div(y2, d2);
+    const R z1 = i2p_div(y1, d1) - l21 * z2;
+    const R z0 = i2p_div(b0, k.a00) - l10 * z1 - l20 * z2;
+    // mujoco_env.py:91-97: (q, v) <- (q + v h, v + a h)
+    const R q0 = y[0] + y[3] * k.dt, q1 = y[1] + y[4] * k.dt, q2 = y[2] + y[5] * k.dt;
+    const R v0 = y[3] + z0 * k.dt, v1 = y[4] + z1 * k.dt, v2 = y[5] + z2 * k.dt;
+    y[0] = q0, y[1] = q1, y[2] = q2, y[3] = v0, y[4] = v1, y[5] = v2;
+    if (z.on)  // mujoco_env.py:98-104: Gaussian state noise after every sub-step
+      add_state_noise<R, 6>(y, z, env, substep0 + static_cast<unsigned long long>(sub));
+  }
+  // inverted_double_pendulum.py:56-60: (theta + pi) % 2 * pi - pi   (sic)
+  o[0] = y[0];
+  o[1] = py_mod(y[1] + k.pi, R(2)) * k.pi - k.pi;
+  o[2] = py_mod(y[2] + k.pi, R(2)) * k.pi - k.pi;
+  o[3] = y[3], o[4] = y[4], o[5] = y[5];
+  // get_batch_reward / get_batch_terminal of the variant on that observation, fused (the expressions of
+  // reward_terminal_kernel's I2P families: inverted_double_pendulum.py:84-90,114-122,150-157,185-196)
+  bool finite = true;
+#pragma unroll
+  for (int j = 0; j < 6; ++j) finite = finite && is_finite(o[j]);
+  const R yy = cos_r(o[1]) + cos_r(o[1] + o[2]);
+  const bool in_rail = (k.x_left < o[0]) && (o[0] < k.x_right);
+  switch (k.variant) {
+    case EMEI_I2P_REBOUND_BALANCING:
+      rew = R(1);
+      notdone = (yy >= R(1.5)) && finite;
+      break;
+    case EMEI_I2P_BOUNDARY_BALANCING:
+      rew = R(1);
+      notdone = (yy >= R(0)) && in_rail && finite;
+      break;
+    case EMEI_I2P_REBOUND_SWINGUP:
+      rew = (R(2) - yy) / R(4);
+      notdone = finite;
+      break;
+    default: {  // EMEI_I2P_BOUNDARY_SWINGUP
+      const R vel_penalty = R(5e-3) * (o[4] * o[4]) + R(1e-4) * (o[5] * o[5]);
+      rew = (R(2) - yy) / R(4) - vel_penalty;
+      notdone = in_rail && finite;
+    } break;
+  }
+}
+
 template <typename R>
 __global__ void __launch_bounds__(kBlock)
     i2p_step_kernel(const R* __restrict__ state_in, R* __restrict__ state_out, R* __restrict__ obs_out,
                     const void* __restrict__ action, R* __restrict__ reward, uint8_t* __restrict__ done, double* stats,
                     int64_t n, const I2PConsts<R> k, const NoiseConsts z) {
   const int64_t stride = static_cast<int64_t>(gridDim.x) * kBlock;
-  const R sign = k.swingup ? R(-1) : R(1);
   double r_acc = 0.0;
   unsigned d_cnt = 0;
   const uintptr_t amask = 2 * sizeof(R) - 1;  // grid-uniform: all three row arrays aligned for 2-element vectors
@@ -129,75 +201,14 @@ __global__ void __launch_bounds__(kBlock)
   pdl_trigger();
   pdl_wait();
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * kBlock + threadIdx.x; i < n; i += stride) {
-    R y[6];
+    R y[6], o[6];
     i2p_load_row<R>(state_in, i, vec2, y);
-    R ctrl = load_ctrl<R>(action, i, k.action_kind);
-    ctrl = ctrl < k.ctrl_low ? k.ctrl_low : (ctrl > k.ctrl_high ? k.ctrl_high : ctrl);  // mj_step clamps ctrl
-    const R F = k.gear * ctrl;
-    for (int sub = 0; sub < k.freq_rate; ++sub) {
-      const R th0 = y[1], th1 = y[2], w0 = y[4], w1 = y[5];
-      R s0, c0, s1, c1, s01, c01;
-      i2p_sincos3<R>(th0, th1, s0, c0, s1, c1, s01, c01);
-      s0 = sign * s0, c0 = sign * c0, s01 = sign * s01, c01 = sign * c01;
-      const R a01 = k.k_a * c0 + k.k_b * c01;
-      const R a02 = k.k_b * c01;
-      const R a11 = k.k_e + R(2) * k.k_c * c1;
-      const R a12 = k.k_c * c1 + k.k_d;
-      const R a22 = k.k_d;
-      const R ws = w0 + w1;
-      const R b0 = F + k.k_a * s0 * (w0 * w0) + k.k_b * s01 * (ws * ws);
-      const R b1 = k.k_g1 * s0 + k.g * k.k_b * s01 + k.k_c * s1 * (w1 * (R(2) * w0 + w1));
-      const R b2 = k.k_b * (k.g * s01 - R(2) * k.l0 * s1 * (w0 * w0));
-      const R l10 = i2p_div(a01, k.a00);
-      const R l20 = i2p_div(a02, k.a00);
-      const R d1 = a11 - l10 * a01;
-      const R t12 = a12 - l10 * a02;
-      const R l21 = i2p_div(t12, d1);
-      const R d2 = a22 - l20 * a02 - l21 * t12;
-      const R y1 = b1 - l10 * b0;
-      const R y2 = b2 - l20 * b0 - l21 * y1;
-      const R z2 = i2p_div(y2, d2);
-      const R z1 = i2p_div(y1, d1) - l21 * z2;
-      const R z0 = i2p_div(b0, k.a00) - l10 * z1 - l20 * z2;
-      // mujoco_env.py:91-97: (q, v) <- (q + v h, v + a h)
-      const R q0 = y[0] + y[3] * k.dt, q1 = y[1] + y[4] * k.dt, q2 = y[2] + y[5] * k.dt;
-      const R v0 = y[3] + z0 * k.dt, v1 = y[4] + z1 * k.dt, v2 = y[5] + z2 * k.dt;
-      y[0] = q0, y[1] = q1, y[2] = q2, y[3] = v0, y[4] = v1, y[5] = v2;
-      if (z.on)  // mujoco_env.py:98-104: Gaussian state noise after every sub-step
-        add_state_noise<R, 6>(y, z, z.env_offset + static_cast<unsigned long long>(i), z.substep0 + static_cast<unsigned long long>(sub));
-    }
-    i2p_store_row<R>(state_out, i, vec2, y);
-    // inverted_double_pendulum.py:56-60: (theta + pi) % 2 * pi - pi   (sic)
-    R o[6] = {y[0], py_mod(y[1] + k.pi, R(2)) * k.pi - k.pi, py_mod(y[2] + k.pi, R(2)) * k.pi - k.pi, y[3], y[4], y[5]};
-    i2p_store_row<R>(obs_out, i, vec2, o);
-    // get_batch_reward / get_batch_terminal of the variant on that observation, fused (the expressions of
-    // reward_terminal_kernel's I2P families: inverted_double_pendulum.py:84-90,114-122,150-157,185-196)
-    bool finite = true;
-#pragma unroll
-    for (int j = 0; j < 6; ++j) finite = finite && is_finite(o[j]);
-    const R yy = cos_r(o[1]) + cos_r(o[1] + o[2]);
-    const bool in_rail = (k.x_left < o[0]) && (o[0] < k.x_right);
+    const R ctrl = load_ctrl<R>(action, i, k.action_kind);
     R rew;
     bool notdone;
-    switch (k.variant) {
-      case EMEI_I2P_REBOUND_BALANCING:
-        rew = R(1);
-        notdone = (yy >= R(1.5)) && finite;
-        break;
-      case EMEI_I2P_BOUNDARY_BALANCING:
-        rew = R(1);
-        notdone = (yy >= R(0)) && in_rail && finite;
-        break;
-      case EMEI_I2P_REBOUND_SWINGUP:
-        rew = (R(2) - yy) / R(4);
-        notdone = finite;
-        break;
-      default: {  // EMEI_I2P_BOUNDARY_SWINGUP
-        const R vel_penalty = R(5e-3) * (o[4] * o[4]) + R(1e-4) * (o[5] * o[5]);
-        rew = (R(2) - yy) / R(4) - vel_penalty;
-        notdone = in_rail && finite;
-      } break;
-    }
+    i2p_env_step<R>(y, ctrl, k, z, z.env_offset + static_cast<unsigned long long>(i), z.substep0, o, rew, notdone);
+    i2p_store_row<R>(state_out, i, vec2, y);
+    i2p_store_row<R>(obs_out, i, vec2, o);
     reward[i] = rew;
     done[i] = notdone ? 0 : 1;
     r_acc += static_cast<double>(rew);

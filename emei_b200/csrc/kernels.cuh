@@ -107,6 +107,83 @@ __device__ __forceinline__ void add_state_noise(R (&y)[DIM], const NoiseConsts& 
   }
 }
 
+// One env step on registers: the whole of BaseControlEnv.step for one env (shared by the step kernel and the
+// reference-arithmetic rollout kernel of rollout_ref.cuh: same bits).  drive = the force (cart-pole family,
+// cartpole.py:121-122,142-143) or the raw control value (IP: clamped to ctrlrange like mj_step, then x gear).
+template <typename R, bool IP>
+__device__ __forceinline__ void cartpole_env_step(Vec4<R>& y, R drive, const CartPoleConsts<R>& k, const NoiseConsts& z,
+                                                  unsigned long long env, unsigned long long substep0, R& rew, bool& notdone,
+                                                  Vec4<R>& obs) {
+  if constexpr (!IP) {
+    // state = [x, x_dot, theta, theta_dot]; base_control.py:71-74
+    const R force = drive;
+    for (int sub = 0; sub < k.freq_rate; ++sub) {
+      R s, c, x_acc, th_acc;
+      sincos_r(y.z, &s, &c);
+      cartpole_accel<R>(y.w, force, s, c, k, x_acc, th_acc);
+      const R nx = euler_cp(y.x, y.y, k), nxd = euler_cp(y.y, x_acc, k);
+      const R nth = euler_cp(y.z, y.w, k), nthd = euler_cp(y.w, th_acc, k);
+      y.x = nx, y.y = nxd, y.z = nth, y.w = nthd;
+    }
+    obs = y;
+    if (k.variant == EMEI_CARTPOLE_SWINGUP) {
+      rew = (cos_r(y.z) + R(1)) / R(2);     // cartpole.py:149-151
+      notdone = abs_r(y.x) < k.x_thr;       // cartpole.py:145-147
+    } else {
+      rew = R(1);                                                     // cartpole.py:128-129
+      notdone = (abs_r(y.z) < k.th_thr) && (abs_r(y.x) < k.x_thr);  // cartpole.py:124-126
+    }
+  } else {
+    // state = [x, theta, v, omega] (qpos||qvel); mujoco_env.py:91-97 forward Euler on the analytic
+    // acceleration; SwingUp models hang the pole down at theta=0 -> theta_cartpole = theta + pi.
+    const bool swingup = (k.variant == EMEI_IP_REBOUND_SWINGUP) || (k.variant == EMEI_IP_BOUNDARY_SWINGUP);
+    const R sign = swingup ? R(-1) : R(1);
+    R ctrl = drive;
+    ctrl = ctrl < k.ctrl_low ? k.ctrl_low : (ctrl > k.ctrl_high ? k.ctrl_high : ctrl);  // mj_step clamps ctrl
+    const R force = k.force_mag * ctrl;  // gear * ctrl (inverted_pendulum.xml:23)
+    for (int sub = 0; sub < k.freq_rate; ++sub) {
+      R s, c, x_acc, th_acc;
+      sincos_r(y.y, &s, &c);
+      s = sign * s;
+      c = sign * c;
+      cartpole_accel<R>(y.w, force, s, c, k, x_acc, th_acc);
+      const R nx = y.x + y.z * k.dt, nth = y.y + y.w * k.dt;
+      const R nv = y.z + x_acc * k.dt, nw = y.w + th_acc * k.dt;
+      y.x = nx, y.y = nth, y.z = nv, y.w = nw;
+      if (z.on) {  // mujoco_env.py:98-104
+        R q[4] = {y.x, y.y, y.z, y.w};
+        add_state_noise<R, 4>(q, z, env, substep0 + static_cast<unsigned long long>(sub));
+        y.x = q[0], y.y = q[1], y.z = q[2], y.w = q[3];
+      }
+    }
+    // observation: theta wrapped, inverted_pendulum.py:45-49
+    const R th_obs = py_mod(y.y + k.pi, k.two_pi) - k.pi;
+    obs = y;
+    obs.y = th_obs;
+    const bool finite = is_finite(y.x) && is_finite(th_obs) && is_finite(y.z) && is_finite(y.w);
+    const R cy = cos_r(th_obs);
+    const bool in_rail = (k.x_left < y.x) && (y.x < k.x_right);
+    switch (k.variant) {
+      case EMEI_IP_REBOUND_BALANCING:  // inverted_pendulum.py:73-79
+        rew = R(1);
+        notdone = (cy >= R(0.9)) && finite;
+        break;
+      case EMEI_IP_BOUNDARY_BALANCING:  // :103-111
+        rew = R(1);
+        notdone = (cy >= R(0)) && in_rail && finite;
+        break;
+      case EMEI_IP_REBOUND_SWINGUP:  // :139-146
+        rew = (R(1) - cy) / R(2);
+        notdone = finite;
+        break;
+      default:  // EMEI_IP_BOUNDARY_SWINGUP :174-183
+        rew = (R(1) - cy) / R(2);
+        notdone = in_rail && finite;
+        break;
+    }
+  }
+}
+
 template <typename R, bool IP>
 __global__ void __launch_bounds__(kBlock)
     cartpole_step_kernel(const R* state_in, R* state_out, R* obs_out, const void* __restrict__ action,
@@ -118,82 +195,13 @@ __global__ void __launch_bounds__(kBlock)
   double r_acc = 0.0;
   unsigned d_cnt = 0;
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * kBlock + threadIdx.x; i < n; i += stride) {
-    Vec4<R> y = Vec4<R>::load(state_in + 4 * i);
+    Vec4<R> y = Vec4<R>::load(state_in + 4 * i), obs;
+    const R drive = IP ? load_ctrl<R>(action, i, k.action_kind) : load_force<R>(action, i, k.action_kind, k.force_mag);
     R rew;
     bool notdone;
-    if constexpr (!IP) {
-      // state = [x, x_dot, theta, theta_dot]; base_control.py:71-74
-      const R force = load_force<R>(action, i, k.action_kind, k.force_mag);
-      for (int sub = 0; sub < k.freq_rate; ++sub) {
-        R s, c, x_acc, th_acc;
-        sincos_r(y.z, &s, &c);
-        cartpole_accel<R>(y.w, force, s, c, k, x_acc, th_acc);
-        const R nx = euler_cp(y.x, y.y, k), nxd = euler_cp(y.y, x_acc, k);
-        const R nth = euler_cp(y.z, y.w, k), nthd = euler_cp(y.w, th_acc, k);
-        y.x = nx, y.y = nxd, y.z = nth, y.w = nthd;
-      }
-      y.store(state_out + 4 * i);
-      if (obs_out != nullptr) y.store(obs_out + 4 * i);
-      if (k.variant == EMEI_CARTPOLE_SWINGUP) {
-        rew = (cos_r(y.z) + R(1)) / R(2);     // cartpole.py:149-151
-        notdone = abs_r(y.x) < k.x_thr;       // cartpole.py:145-147
-      } else {
-        rew = R(1);                                                     // cartpole.py:128-129
-        notdone = (abs_r(y.z) < k.th_thr) && (abs_r(y.x) < k.x_thr);  // cartpole.py:124-126
-      }
-    } else {
-      // state = [x, theta, v, omega] (qpos||qvel); mujoco_env.py:91-97 forward Euler on the analytic
-      // acceleration; SwingUp models hang the pole down at theta=0 -> theta_cartpole = theta + pi.
-      const bool swingup = (k.variant == EMEI_IP_REBOUND_SWINGUP) || (k.variant == EMEI_IP_BOUNDARY_SWINGUP);
-      const R sign = swingup ? R(-1) : R(1);
-      R ctrl = load_ctrl<R>(action, i, k.action_kind);
-      ctrl = ctrl < k.ctrl_low ? k.ctrl_low : (ctrl > k.ctrl_high ? k.ctrl_high : ctrl);  // mj_step clamps ctrl
-      const R force = k.force_mag * ctrl;  // gear * ctrl (inverted_pendulum.xml:23)
-      for (int sub = 0; sub < k.freq_rate; ++sub) {
-        R s, c, x_acc, th_acc;
-        sincos_r(y.y, &s, &c);
-        s = sign * s;
-        c = sign * c;
-        cartpole_accel<R>(y.w, force, s, c, k, x_acc, th_acc);
-        const R nx = y.x + y.z * k.dt, nth = y.y + y.w * k.dt;
-        const R nv = y.z + x_acc * k.dt, nw = y.w + th_acc * k.dt;
-        y.x = nx, y.y = nth, y.z = nv, y.w = nw;
-        if (z.on) {  // mujoco_env.py:98-104
-          R q[4] = {y.x, y.y, y.z, y.w};
-          add_state_noise<R, 4>(q, z, z.env_offset + static_cast<unsigned long long>(i), z.substep0 + static_cast<unsigned long long>(sub));
-          y.x = q[0], y.y = q[1], y.z = q[2], y.w = q[3];
-        }
-      }
-      y.store(state_out + 4 * i);
-      // observation: theta wrapped, inverted_pendulum.py:45-49
-      const R th_obs = py_mod(y.y + k.pi, k.two_pi) - k.pi;
-      if (obs_out != nullptr) {
-        Vec4<R> o = y;
-        o.y = th_obs;
-        o.store(obs_out + 4 * i);
-      }
-      const bool finite = is_finite(y.x) && is_finite(th_obs) && is_finite(y.z) && is_finite(y.w);
-      const R cy = cos_r(th_obs);
-      const bool in_rail = (k.x_left < y.x) && (y.x < k.x_right);
-      switch (k.variant) {
-        case EMEI_IP_REBOUND_BALANCING:  // inverted_pendulum.py:73-79
-          rew = R(1);
-          notdone = (cy >= R(0.9)) && finite;
-          break;
-        case EMEI_IP_BOUNDARY_BALANCING:  // :103-111
-          rew = R(1);
-          notdone = (cy >= R(0)) && in_rail && finite;
-          break;
-        case EMEI_IP_REBOUND_SWINGUP:  // :139-146
-          rew = (R(1) - cy) / R(2);
-          notdone = finite;
-          break;
-        default:  // EMEI_IP_BOUNDARY_SWINGUP :174-183
-          rew = (R(1) - cy) / R(2);
-          notdone = in_rail && finite;
-          break;
-      }
-    }
+    cartpole_env_step<R, IP>(y, drive, k, z, z.env_offset + static_cast<unsigned long long>(i), z.substep0, rew, notdone, obs);
+    y.store(state_out + 4 * i);
+    if (obs_out != nullptr) obs.store(obs_out + 4 * i);
     reward[i] = rew;
     done[i] = notdone ? 0 : 1;
     r_acc += static_cast<double>(rew);
@@ -283,6 +291,60 @@ __device__ __forceinline__ R cb_get_angle(R x, R y, const ChargedBallConsts<R>& 
 
 // F32FORCE (double only): the reference's continuous variant under numpy>=2 evaluates every
 // `python_float (op) np.float32` of _get_update_info in float32 (see oracle/emei_oracle.py).
+// One env step on registers (shared by the step kernel and the reference-arithmetic rollout kernel); returns the reward.
+template <typename R, bool F32FORCE>
+__device__ __forceinline__ R charged_ball_env_step(bool& on, R& theta, R& omega, Vec4<R>& f, R E, const ChargedBallConsts<R>& k) {
+  [[maybe_unused]] const float E32 = static_cast<float>(E);
+  const R gravity = k.m * k.g;
+  for (int sub = 0; sub < k.freq_rate; ++sub) {
+    if (on) {
+      // _get_update_info :72-78 + update_state :56-61 + circle_to_free :25-28
+      R s, c;
+      sincos_r(theta, &s, &c);
+      const R centrifugal = k.m * (omega * omega) * k.r;
+      R theta_acc;
+      bool flag;
+      if constexpr (F32FORCE) {
+        const float t = __fadd_rn(static_cast<float>(s * gravity), __fmul_rn(static_cast<float>(c), E32));
+        theta_acc = static_cast<R>(__fdiv_rn(t, static_cast<float>(k.m * k.r)));
+        flag = centrifugal + static_cast<R>(__fmul_rn(static_cast<float>(s), E32)) < c * gravity;
+      } else {
+        theta_acc = (s * gravity + c * E) / (k.m * k.r);
+        flag = centrifugal + s * E < c * gravity;
+      }
+      const R theta_n = theta + omega * k.h;
+      const R omega_n = omega + theta_acc * k.h;
+      theta = theta_n, omega = omega_n;
+      R sn, cn;
+      sincos_r(theta, &sn, &cn);
+      f.x = sn * k.r;
+      f.y = cn * k.r;
+      f.z = omega * f.y;
+      f.w = -omega * f.x;
+      if (flag) on = false;
+    } else {
+      // _get_update_info :79-82 + update_state :62-66 + free_to_circle :44-52
+      R acc_x;
+      if constexpr (F32FORCE)
+        acc_x = static_cast<R>(__fdiv_rn(E32, static_cast<float>(k.m)));
+      else
+        acc_x = E / k.m;
+      const R nx = f.x + f.z * k.h, ny = f.y + f.w * k.h;
+      const R nvx = f.z + acc_x * k.h, nvy = f.w + (-k.g) * k.h;
+      f.x = nx, f.y = ny, f.z = nvx, f.w = nvy;
+      if (f.x * f.x + f.y * f.y > k.land_thr) {
+        on = true;
+        theta = cb_get_angle<R>(f.x, f.y, k);
+        const R v_angle = cb_get_angle<R>(f.z, f.w, k);
+        const bool greater = (abs_r(v_angle - theta) < k.pi) ? (v_angle > theta) : (v_angle < theta);  // :38-42
+        const R speed = sqrt_r(f.z * f.z + f.w * f.w) / k.r;
+        omega = greater ? speed : -speed;
+      }
+    }
+  }
+  return R(1) - sqrt_r(f.x * f.x + f.y * f.y) / k.r;  // charged_ball.py:158-160
+}
+
 template <typename R, bool F32FORCE>
 __global__ void __launch_bounds__(kBlock)
     charged_ball_step_kernel(uint8_t* on_circle, R* circle, R* free_state, const void* __restrict__ action,
@@ -302,61 +364,13 @@ __global__ void __launch_bounds__(kBlock)
     }
     Vec4<R> f = Vec4<R>::load(free_state + 4 * i);  // x, y, vx, vy
     const R E = load_force<R>(action, i, k.action_kind, k.charge);  // charged_ball.py:155-156,169-170
-    [[maybe_unused]] const float E32 = static_cast<float>(E);
-    const R gravity = k.m * k.g;
-    for (int sub = 0; sub < k.freq_rate; ++sub) {
-      if (on) {
-        // _get_update_info :72-78 + update_state :56-61 + circle_to_free :25-28
-        R s, c;
-        sincos_r(theta, &s, &c);
-        const R centrifugal = k.m * (omega * omega) * k.r;
-        R theta_acc;
-        bool flag;
-        if constexpr (F32FORCE) {
-          const float t = __fadd_rn(static_cast<float>(s * gravity), __fmul_rn(static_cast<float>(c), E32));
-          theta_acc = static_cast<R>(__fdiv_rn(t, static_cast<float>(k.m * k.r)));
-          flag = centrifugal + static_cast<R>(__fmul_rn(static_cast<float>(s), E32)) < c * gravity;
-        } else {
-          theta_acc = (s * gravity + c * E) / (k.m * k.r);
-          flag = centrifugal + s * E < c * gravity;
-        }
-        const R theta_n = theta + omega * k.h;
-        const R omega_n = omega + theta_acc * k.h;
-        theta = theta_n, omega = omega_n;
-        R sn, cn;
-        sincos_r(theta, &sn, &cn);
-        f.x = sn * k.r;
-        f.y = cn * k.r;
-        f.z = omega * f.y;
-        f.w = -omega * f.x;
-        if (flag) on = false;
-      } else {
-        // _get_update_info :79-82 + update_state :62-66 + free_to_circle :44-52
-        R acc_x;
-        if constexpr (F32FORCE)
-          acc_x = static_cast<R>(__fdiv_rn(E32, static_cast<float>(k.m)));
-        else
-          acc_x = E / k.m;
-        const R nx = f.x + f.z * k.h, ny = f.y + f.w * k.h;
-        const R nvx = f.z + acc_x * k.h, nvy = f.w + (-k.g) * k.h;
-        f.x = nx, f.y = ny, f.z = nvx, f.w = nvy;
-        if (f.x * f.x + f.y * f.y > k.land_thr) {
-          on = true;
-          theta = cb_get_angle<R>(f.x, f.y, k);
-          const R v_angle = cb_get_angle<R>(f.z, f.w, k);
-          const bool greater = (abs_r(v_angle - theta) < k.pi) ? (v_angle > theta) : (v_angle < theta);  // :38-42
-          const R speed = sqrt_r(f.z * f.z + f.w * f.w) / k.r;
-          omega = greater ? speed : -speed;
-        }
-      }
-    }
+    const R rew = charged_ball_env_step<R, F32FORCE>(on, theta, omega, f, E, k);
     on_circle[i] = on ? 1 : 0;
     if constexpr (sizeof(R) == 4)
       reinterpret_cast<float2*>(circle)[i] = make_float2(theta, omega);
     else
       reinterpret_cast<double2*>(circle)[i] = make_double2(theta, omega);
     f.store(free_state + 4 * i);
-    const R rew = R(1) - sqrt_r(f.x * f.x + f.y * f.y) / k.r;  // charged_ball.py:158-160
     reward[i] = rew;
     done[i] = 0;  // charged_ball.py:110-111
     r_acc += static_cast<double>(rew);

@@ -66,10 +66,16 @@ class StepOutputs:
 
 
 class RolloutMixin:
-    """Episode bookkeeping buffers + the call of a fused T-step rollout entry point (emei_*_rollout_f32)."""
+    """Episode bookkeeping buffers + the call of a fused T-step rollout entry point.
+
+    float32 without state noise: the packed kernels (emei_cartpole_rollout_f32 / emei_charged_ball_rollout_f32).
+    float64 (reference-exact), the inverted double pendulum and obs_noise_params: the reference-arithmetic kernels
+    (emei_cartpole_rollout_ref_* / emei_i2p_rollout_* / emei_charged_ball_rollout_ref_f64), one env per thread, the
+    step entry points' own device functions -- records, rewards and episode returns then have the engine dtype."""
 
     ep_step = ep_return = ep_index = None
     t_global = 0
+    obs_dim = 4
 
     def _alloc_episode(self):
         if self.ep_step is None:
@@ -88,12 +94,18 @@ class RolloutMixin:
                 self.ep_index.zero_()
                 self.t_global = 0
 
-    def _rollout(self, entry: str, state_ptrs, rp: _lib.RolloutParams, actions, record: bool, rollout_stats: torch.Tensor):
+    def _rollout(self, entry: str, state_ptrs, rp: _lib.RolloutParams, actions, record: bool, rollout_stats: torch.Tensor,
+                 ref: bool = False, extra=()):
+        """entry: C-ABI symbol (with the precision suffix); ref: a reference-arithmetic entry point (records, rewards
+        and episode returns in the engine dtype); extra: its trailing arguments before the stream (noise / init tables)."""
         env = self.env
-        if env.dtype != torch.float32:
-            raise NotImplementedError("the fused rollout kernel is float32 (use step() for the float64 reference-exact mode)")
+        if env.dtype != torch.float32 and not ref:
+            raise NotImplementedError("the packed rollout kernels are float32")
         self._alloc_episode()
-        T, n, dev = int(rp.horizon), self.n, env.device
+        rdt = env.dtype if ref else torch.float32
+        if self.ep_return.dtype != rdt:  # the running return follows the kernel's real type
+            self.ep_return = self.ep_return.to(rdt)
+        T, n, dev, D = int(rp.horizon), self.n, env.device, self.obs_dim
         rp.t0 = self.t_global
         rec = {}
         if actions is not None:
@@ -109,10 +121,10 @@ class RolloutMixin:
         ptrs = [None] * 6
         if record:
             rec = dict(
-                observations=torch.empty((T, n, 4), dtype=torch.float32, device=dev),
-                next_observations=torch.empty((T, n, 4), dtype=torch.float32, device=dev),
+                observations=torch.empty((T, n, D), dtype=rdt, device=dev),
+                next_observations=torch.empty((T, n, D), dtype=rdt, device=dev),
                 actions=torch.empty((T, n), dtype=act_dtype, device=dev),
-                rewards=torch.empty((T, n), dtype=torch.float32, device=dev),
+                rewards=torch.empty((T, n), dtype=rdt, device=dev),
                 dones=torch.empty((T, n), dtype=torch.uint8, device=dev),
                 timeouts=torch.empty((T, n), dtype=torch.uint8, device=dev),
             )
@@ -121,7 +133,7 @@ class RolloutMixin:
             _lib.call(
                 entry, *state_ptrs, self.ep_step.data_ptr(), self.ep_return.data_ptr(), self.ep_index.data_ptr(),
                 actions.data_ptr() if actions is not None else None, *ptrs,
-                rollout_stats.data_ptr(), n, ctypes.byref(self.params), ctypes.byref(rp), env._stream(),
+                rollout_stats.data_ptr(), n, ctypes.byref(self.params), ctypes.byref(rp), *extra, env._stream(),
             )
         self.t_global += T
         if record:
@@ -217,10 +229,15 @@ class CartPoleEngine(RolloutMixin):
         self._cur = 1 - self._cur
 
     # ---- fused T-step rollout (emei_cartpole_rollout_f32) ----------------------------------------
-    def rollout(self, rp: _lib.RolloutParams, actions, record: bool, rollout_stats: torch.Tensor):
+    def rollout(self, rp: _lib.RolloutParams, actions, record: bool, rollout_stats: torch.Tensor, noise=None):
         self._alloc()
         state = self._bufs[self._cur]
-        return self._rollout("emei_cartpole_rollout_f32", [state.data_ptr()], rp, actions, record, rollout_stats)
+        if self.env.dtype == torch.float32 and noise is None:
+            return self._rollout("emei_cartpole_rollout_f32", [state.data_ptr()], rp, actions, record, rollout_stats)
+        # float64 reference-exact mode / obs_noise_params: the step entry points' own arithmetic, one env per thread
+        z = ctypes.byref(noise) if noise is not None else None
+        return self._rollout("emei_cartpole_rollout_ref" + self.env._suffix, [state.data_ptr()], rp, actions, record, rollout_stats,
+                             ref=True, extra=(z,))
 
     def next_obs_stateless(self, obs: torch.Tensor, action: torch.Tensor):
         """get_batch_next_obs: one dynamics step from caller-supplied observations (any batch size);
@@ -255,8 +272,21 @@ class CartPoleEngine(RolloutMixin):
         self.has_state = True
 
 
-class I2PEngine:
+class I2PEngine(RolloutMixin):
     """analytic inverted double pendulum (emei_i2p_step_*): state [B,6] ping-pong pair + observation buffers."""
+
+    obs_dim = 6
+
+    def rollout(self, rp: _lib.RolloutParams, actions, record: bool, rollout_stats: torch.Tensor, noise=None):
+        """emei_i2p_rollout_*: the four I2P tasks of zoo/conf/task/BI2P*.yaml through the collection loop of
+        zoo/util.py:33-93, one launch; in-kernel resets = reset_model (init_qpos || init_qvel + N(0, sigma))."""
+        self._alloc()
+        state = self._bufs[self._cur]
+        mean, sigma = self.env._init_tables()
+        Arr = ctypes.c_double * 6
+        z = ctypes.byref(noise) if noise is not None else None
+        return self._rollout("emei_i2p_rollout" + self.env._suffix, [state.data_ptr()], rp, actions, record, rollout_stats,
+                             ref=True, extra=(Arr(*mean), Arr(*sigma), z))
 
     def __init__(self, env, params: _lib.I2PParams):
         self.env = env
@@ -284,6 +314,7 @@ class I2PEngine:
             raise ValueError(f"state must have shape {(self.n, 6)}, got {tuple(s.shape)}")
         self._bufs[self._cur].copy_(s)
         self.has_state = True
+        self.new_episodes(reseed=False)
 
     def step(self, action: torch.Tensor, copy_obs: bool, noise: Optional[_lib.NoiseParams] = None):
         env = self.env
@@ -302,6 +333,33 @@ class I2PEngine:
             env._call("emei_i2p_step_noisy", *ptrs, ctypes.byref(noise), env._stream())
         self._cur = nxt
         return obs, reward, done.view(torch.bool)
+
+    def step_range(self, lo: int, hi: int, action: torch.Tensor, reward: torch.Tensor, done: torch.Tensor, obs_out,
+                   noise: Optional[_lib.NoiseParams] = None):
+        """Launch the step kernel for envs [lo, hi) only (src -> dst of the CURRENT ping-pong pair, no flip): the
+        building block of the chunked host pipeline (``step_host``).  Call ``flip()`` once all ranges are launched."""
+        env = self.env
+        self._alloc()
+        nxt = 1 - self._cur
+        src, dst = self._bufs[self._cur], self._bufs[nxt]
+        if obs_out is None:
+            obs_out = self._obs[nxt]
+        self.params.action_kind = _ACTION_KIND[action.dtype]
+        es, ea = src.element_size() * 6, action.element_size()
+        ptrs = (src.data_ptr() + lo * es, dst.data_ptr() + lo * es, obs_out.data_ptr() + lo * es, action.data_ptr() + lo * ea,
+                reward.data_ptr() + lo * reward.element_size(), done.data_ptr() + lo, env.stats.data_ptr(), hi - lo,
+                ctypes.byref(self.params))
+        if noise is None:
+            env._call("emei_i2p_step", *ptrs, env._stream())
+        else:
+            z = _lib.NoiseParams()
+            ctypes.memmove(ctypes.byref(z), ctypes.byref(noise), ctypes.sizeof(z))
+            z.env_offset = noise.env_offset + lo
+            env._call("emei_i2p_step_noisy", *ptrs, ctypes.byref(z), env._stream())
+        return obs_out
+
+    def flip(self):
+        self._cur = 1 - self._cur
 
     def next_obs_stateless(self, obs: torch.Tensor, action: torch.Tensor):
         """get_batch_next_obs: one dynamics step from caller-supplied STATES (the 6-d observation of this family
@@ -333,9 +391,11 @@ class I2PEngine:
 class ChargedBallEngine(RolloutMixin):
     """charged ball (emei_charged_ball_step_*): three state arrays updated in place."""
 
-    def rollout(self, rp: _lib.RolloutParams, actions, record: bool, rollout_stats: torch.Tensor):
+    def rollout(self, rp: _lib.RolloutParams, actions, record: bool, rollout_stats: torch.Tensor, noise=None):
         ptrs = [self.on_circle.data_ptr(), self.circle.data_ptr(), self.free.data_ptr()]
-        return self._rollout("emei_charged_ball_rollout_f32", ptrs, rp, actions, record, rollout_stats)
+        if self.env.dtype == torch.float32:
+            return self._rollout("emei_charged_ball_rollout_f32", ptrs, rp, actions, record, rollout_stats)
+        return self._rollout("emei_charged_ball_rollout_ref_f64", ptrs, rp, actions, record, rollout_stats, ref=True)
 
     def __init__(self, env, params: _lib.ChargedBallParams):
         self.env = env
@@ -597,8 +657,11 @@ class HostStaging:
         edges[-1] = n                                             # of a range (uint8 flags included) stays 16-byte aligned
         return [(edges[i], edges[i + 1]) for i in range(len(edges) - 1) if edges[i + 1] > edges[i]]
 
+    ALL_OUTPUTS = ("obs", "reward", "done")
+
     def __init__(self, env, chunks: Optional[int] = None, fractions=None):
         self.env = env
+        self.outputs = self.ALL_OUTPUTS  # which results the current call downloads
         n = env.num_envs
         cont = len(env.action_space.shape) > 0
         dev = env.device
@@ -611,7 +674,9 @@ class HostStaging:
         self.rew_dev = torch.empty((n, 1), dtype=env.dtype, device=dev)
         self.done_dev = torch.empty((n, 1), dtype=torch.uint8, device=dev)
         self.h2d_bytes = self.a_host.numel() * self.a_host.element_size()
-        self.d2h_bytes = sum(t.numel() * t.element_size() for t in (self.obs_host, self.rew_host, self.done_host))
+        self._out_bytes = {"obs": self.obs_host.numel() * self.obs_host.element_size(),
+                           "reward": self.rew_host.numel() * self.rew_host.element_size(), "done": self.done_host.numel()}
+        self.d2h_bytes = sum(self._out_bytes.values())
         self.ranges = self.plan_ranges(n, chunks, fractions)
         self.streams = [torch.cuda.Stream(dev) for _ in self.ranges]
         self.done_host_u8 = self.done_host.view(torch.uint8)
@@ -626,12 +691,16 @@ class HostStaging:
         env, eng = self.env, self.env._engine
         cur = torch.cuda.current_stream(env.device)
         kw = {} if noise is None else {"noise": noise}
+        want = self.outputs
         if len(self.ranges) == 1:  # small batch: latency-bound, no side streams
             self.a_dev.copy_(a_src, non_blocking=True)
             obs = eng.step_range(0, env.num_envs, self.a_dev, self.rew_dev, self.done_dev, None, **kw)
-            self.obs_host.copy_(obs, non_blocking=True)
-            self.rew_host.copy_(self.rew_dev, non_blocking=True)
-            self.done_host_u8.copy_(self.done_dev, non_blocking=True)
+            if "obs" in want:
+                self.obs_host.copy_(obs, non_blocking=True)
+            if "reward" in want:
+                self.rew_host.copy_(self.rew_dev, non_blocking=True)
+            if "done" in want:
+                self.done_host_u8.copy_(self.done_dev, non_blocking=True)
             return
         start = torch.cuda.Event()
         start.record(cur)
@@ -640,14 +709,26 @@ class HostStaging:
                 st.wait_event(start)  # everything queued before this call (reset, set_state, ...) is visible
                 self.a_dev[lo:hi].copy_(a_src[lo:hi], non_blocking=True)
                 obs = eng.step_range(lo, hi, self.a_dev, self.rew_dev, self.done_dev, None, **kw)
-                self.obs_host[lo:hi].copy_(obs[lo:hi], non_blocking=True)
-                self.rew_host[lo:hi].copy_(self.rew_dev[lo:hi], non_blocking=True)
-                self.done_host_u8[lo:hi].copy_(self.done_dev[lo:hi], non_blocking=True)
+                if "obs" in want:
+                    self.obs_host[lo:hi].copy_(obs[lo:hi], non_blocking=True)
+                if "reward" in want:
+                    self.rew_host[lo:hi].copy_(self.rew_dev[lo:hi], non_blocking=True)
+                if "done" in want:
+                    self.done_host_u8[lo:hi].copy_(self.done_dev[lo:hi], non_blocking=True)
         for st in self.streams:
             cur.wait_stream(st)
 
-    def step(self, action):
-        """Eager the first time a (caller buffer, ping-pong parity) pair is seen; captured into a CUDA graph the
+    def _result(self):
+        w = self.outputs
+        return (self.obs_host.numpy() if "obs" in w else None, self.rew_host.numpy() if "reward" in w else None,
+                self.done_host.numpy() if "done" in w else None, False, {})
+
+    def step(self, action, outputs=None):
+        """``outputs``: subset of ("obs", "reward", "done") to download (default: all three, the reference's step()
+        contract); what is not asked for stays on the device (``env.state``) and comes back as None -- a caller that
+        only consumes reward / done moves 5 bytes per env over PCIe instead of 21.
+
+        Eager the first time a (caller buffer, ping-pong parity) pair is seen; captured into a CUDA graph the
         second time and replayed from then on: a host step is ~5 enqueues per range, and at 2^20 envs the host
         could not queue them as fast as PCIe drains them (0.52 ms per step against 0.42 ms of copies); one graph
         launch also lets the ranges be finer.  The graph bakes pointers in, so it is keyed by the action buffer's
@@ -655,6 +736,11 @@ class HostStaging:
         env = self.env
         eng = env._engine
         assert eng is not None and eng.has_state, "Call reset before using step method."
+        outs = self.ALL_OUTPUTS if outputs is None else tuple(o for o in self.ALL_OUTPUTS if o in outputs)
+        if outputs is not None and (len(outs) != len(tuple(outputs)) or not outs):
+            raise ValueError(f"outputs must be a non-empty subset of {self.ALL_OUTPUTS}, got {outputs!r}")
+        self.outputs = outs
+        self.d2h_bytes = sum(self._out_bytes[o] for o in outs)
         a = torch.as_tensor(action)
         if a.is_cuda:
             raise TypeError("step_host takes host actions; use step() for device tensors")
@@ -677,8 +763,8 @@ class HostStaging:
             self._enqueue(a_src, noise)
             eng.flip()
             cur.synchronize()
-            return self.obs_host.numpy(), self.rew_host.numpy(), self.done_host.numpy(), False, {}
-        key = (a_src.data_ptr(), getattr(eng, "_cur", 0))
+            return self._result()
+        key = (a_src.data_ptr(), getattr(eng, "_cur", 0), outs)
         graph = self._graphs.get(key) if self.use_graphs else None
         if graph is None and self.use_graphs and self._seen.get(key, 0) >= 1 and len(self._graphs) < 32:
             graph = torch.cuda.CUDAGraph()
@@ -707,4 +793,4 @@ class HostStaging:
             self._enqueue(a_src)
         eng.flip()
         cur.synchronize()
-        return self.obs_host.numpy(), self.rew_host.numpy(), self.done_host.numpy(), False, {}
+        return self._result()

@@ -70,6 +70,12 @@ class BaseInvertedDoublePendulumEnv(EmeiMujocoEnv):
         p.dt, p.freq_rate, p.variant = self.real_time_scale, self.freq_rate, self._family
         return p
 
+    def _rollout_params(self) -> _lib.RolloutParams:
+        rp = _lib.RolloutParams()
+        rp.init_kind, rp.init_pi_column = 1, -1  # reset_model: init_qpos/qvel + N(0, sigma) (mujoco_env.py:130-140); 6-d tables travel separately
+        rp.action_low, rp.action_high = float(self.action_space.low[0]), float(self.action_space.high[0])
+        return rp
+
     def _ensure_engine(self):
         if self._family is None:
             raise NotImplementedError("BaseInvertedDoublePendulumEnv is abstract")
@@ -99,6 +105,7 @@ class BaseInvertedDoublePendulumEnv(EmeiMujocoEnv):
         self._reseed(seed)
         self._noise_step = 0
         self.state = self._sample_init_obs(self.num_envs)  # reset_model: mujoco_env.py:130-135 (returns qpos||qvel)
+        self._engine.new_episodes(reseed=True)
         return self.state.clone(), {}
 
     def step(self, action):

@@ -103,7 +103,12 @@ class EmeiMujocoEnv(EmeiEnv):
         sp, sv = self._noise_sigmas(self.obs_noise_params)
         return bool(np.any(sp != 0) or np.any(sv != 0))
 
-    def _next_obs_noise(self) -> Optional[_lib.NoiseParams]:
+    def _init_tables(self):
+        """(mean[nq+nv], sigma[nq+nv]) of reset_model: init_qpos || init_qvel and the per-coordinate init noise."""
+        sp, sv = self._noise_sigmas(self.init_noise_params)
+        return np.concatenate([self.init_qpos, self.init_qvel]), np.concatenate([sp, sv])
+
+    def _next_obs_noise(self, advance: int = 1) -> Optional[_lib.NoiseParams]:
         """NoiseParams of the NEXT step call (None when obs_noise_params is zero): per-coordinate sigmas
         (scalar / (pos, vel) / {jnt_id: (pos, vel)} forms of mujoco_env.py:217-227), a Philox key derived from
         ``reset(seed=)`` and the env-step counter, which ``reset`` zeroes."""
@@ -116,7 +121,7 @@ class EmeiMujocoEnv(EmeiEnv):
         z.seed = (self._seed * 0xA24BAED4963EE407 + 0x9FB21C651E98DF25 + max(self._rollout_epoch, 0) * 0x8EBC6AF09C88C6E3) & 0xFFFFFFFFFFFFFFFF
         z.env_offset = self.env_offset
         z.step = self._noise_step
-        self._noise_step += 1
+        self._noise_step += int(advance)  # a fused rollout consumes one step index per env step
         return z
 
     def get_batch_init_state(self, batch_size):

@@ -227,6 +227,55 @@ int emei_charged_ball_rollout_f32(uint8_t* on_circle_io, float* circle_io, float
                                   float* rec_rewards, uint8_t* rec_dones, uint8_t* rec_timeouts, double* stats, int64_t n,
                                   const emei_charged_ball_params* p, const emei_rollout_params* r, emei_stream_t stream);
 
+/* ---- fused rollouts in the arithmetic of the step entry points (both precisions) -------------------------
+ * Same contract as emei_cartpole_rollout_f32 (zoo/util.py:33-93 batched: policy, step, TimeLimit, auto-reset, optional
+ * records, six statistics) for what the packed float32 kernels do not cover: the float64 reference-exact mode, the
+ * analytic inverted double pendulum (the four I2P tasks of zoo/conf/task/BI2P*.yaml) and obs_noise_params (Gaussian
+ * state noise after every sub-step, mujoco_env.py:98-104).  One env per thread; per step the arithmetic is the device
+ * function the step kernel calls:
+ *   emei_cartpole_rollout_ref_f64 == horizon x emei_cartpole_step_f64   (z == NULL) / emei_ip_step_noisy_f64 (z != NULL)
+ *   emei_cartpole_rollout_ref_f32 == horizon x emei_ip_step_noisy_f32   (z != NULL, EMEI_IP_* variants; with z == NULL it
+ *        is the plain float32 evaluation of the reference's expressions, NOT the lean emei_cartpole_step_f32 bits --
+ *        use emei_cartpole_rollout_f32 for those)
+ *   emei_i2p_rollout_{f32,f64}    == horizon x emei_i2p_step_* / emei_i2p_step_noisy_*
+ *   emei_charged_ball_rollout_ref_f64 == horizon x emei_charged_ball_step_f64 (the _f32 symbol is the plain float32
+ *        evaluation; emei_charged_ball_rollout_f32 is the one that equals emei_charged_ball_step_f32)
+ * bit for bit, plus the bookkeeping.  z->step = env-step counter of the FIRST step of the call (step t uses step + t).
+ * In-kernel resets: the arithmetic of emei_init_uniform / emei_init_gaussian / emei_init_charged_ball in this precision
+ * with seed = r->seed_reset + episode_index * 0xD1B54A32D192ED03.  Records and episode_return_io have the real type;
+ * observations are [T, n, D] with D = 4 (6 for I2P: current_obs, inverted_double_pendulum.py:56-60).
+ * I2P: init_mean / init_sigma are HOST arrays of 6 (reset_model: init_qpos || init_qvel, noise per coordinate). */
+int emei_cartpole_rollout_ref_f32(float* state_io, int32_t* episode_step_io, float* episode_return_io, int32_t* episode_index_io,
+                                  const void* actions, float* rec_observations, float* rec_next_observations, void* rec_actions,
+                                  float* rec_rewards, uint8_t* rec_dones, uint8_t* rec_timeouts, double* stats, int64_t n,
+                                  const emei_cartpole_params* p, const emei_rollout_params* r, const emei_noise_params* z,
+                                  emei_stream_t stream);
+int emei_cartpole_rollout_ref_f64(double* state_io, int32_t* episode_step_io, double* episode_return_io, int32_t* episode_index_io,
+                                  const void* actions, double* rec_observations, double* rec_next_observations, void* rec_actions,
+                                  double* rec_rewards, uint8_t* rec_dones, uint8_t* rec_timeouts, double* stats, int64_t n,
+                                  const emei_cartpole_params* p, const emei_rollout_params* r, const emei_noise_params* z,
+                                  emei_stream_t stream);
+int emei_i2p_rollout_f32(float* state_io, int32_t* episode_step_io, float* episode_return_io, int32_t* episode_index_io,
+                         const void* actions, float* rec_observations, float* rec_next_observations, void* rec_actions,
+                         float* rec_rewards, uint8_t* rec_dones, uint8_t* rec_timeouts, double* stats, int64_t n,
+                         const emei_i2p_params* p, const emei_rollout_params* r, const double* init_mean, const double* init_sigma,
+                         const emei_noise_params* z, emei_stream_t stream);
+int emei_i2p_rollout_f64(double* state_io, int32_t* episode_step_io, double* episode_return_io, int32_t* episode_index_io,
+                         const void* actions, double* rec_observations, double* rec_next_observations, void* rec_actions,
+                         double* rec_rewards, uint8_t* rec_dones, uint8_t* rec_timeouts, double* stats, int64_t n,
+                         const emei_i2p_params* p, const emei_rollout_params* r, const double* init_mean, const double* init_sigma,
+                         const emei_noise_params* z, emei_stream_t stream);
+int emei_charged_ball_rollout_ref_f32(uint8_t* on_circle_io, float* circle_io, float* free_state_io, int32_t* episode_step_io,
+                                      float* episode_return_io, int32_t* episode_index_io, const void* actions,
+                                      float* rec_observations, float* rec_next_observations, void* rec_actions, float* rec_rewards,
+                                      uint8_t* rec_dones, uint8_t* rec_timeouts, double* stats, int64_t n,
+                                      const emei_charged_ball_params* p, const emei_rollout_params* r, emei_stream_t stream);
+int emei_charged_ball_rollout_ref_f64(uint8_t* on_circle_io, double* circle_io, double* free_state_io, int32_t* episode_step_io,
+                                      double* episode_return_io, int32_t* episode_index_io, const void* actions,
+                                      double* rec_observations, double* rec_next_observations, void* rec_actions, double* rec_rewards,
+                                      uint8_t* rec_dones, uint8_t* rec_timeouts, double* stats, int64_t n,
+                                      const emei_charged_ball_params* p, const emei_rollout_params* r, emei_stream_t stream);
+
 /* ---- model-based scoring: get_batch_reward + get_batch_terminal fused ------------------------- */
 typedef struct emei_scoring_params {
   int32_t family;                  /* EMEI_* family id */
