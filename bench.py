@@ -372,6 +372,13 @@ class CartPoleStep(Workload):
     def step_e2e(self, i):
         self.env0.step_host(self.act_host[i % len(self.act_host)])
 
+    # the same host step for a caller that consumes reward and done only (evaluation of a policy's return): the
+    # observation stays on the device -- 5 bytes per env come back instead of 21
+    e2e_light_api = "env.step_host(action_host, outputs=('reward', 'done')) -> numpy reward/terminated; obs stays on the device"
+
+    def step_e2e_light(self, i):
+        self.env0.step_host(self.act_host[i % len(self.act_host)], outputs=("reward", "done"))
+
     @classmethod
     def config(cls, args, world):
         ring = args.ring or cls.ring
@@ -1082,13 +1089,26 @@ def measure(wl, ctx, K, W, args, want_e2e=True):
         launch_mode = "stream"
     launches0 = _lib.launch_count
     graph = None
+    ev_in = None
     if launch_mode == "graph":  # launch-bound steps: K launches captured once, replayed as one graph
         graph = torch.cuda.CUDAGraph()
         side = torch.cuda.Stream(dev)
+        # the timing events are NODES of the graph (cudaEventRecordExternal), immediately before the first step kernel
+        # and after the last: they bracket exactly the K steps on the device.  Events recorded around graph.replay()
+        # additionally contain the graph's own launch (a one-off of ~5-10 us, 3-5 % of a 20-step region, nothing at
+        # K = 2000); that figure is reported beside it (protocol.ms_per_step_including_graph_launch).
+        try:
+            ev_in = (torch.cuda.Event(enable_timing=True, external=True), torch.cuda.Event(enable_timing=True, external=True))
+        except TypeError:
+            ev_in = None
         with torch.cuda.stream(side):
             with torch.cuda.graph(graph, stream=side):
+                if ev_in is not None:
+                    ev_in[0].record()
                 for i in range(K):
                     wl.step(i)
+                if ev_in is not None:
+                    ev_in[1].record()
         launches = _lib.launch_count - launches0
     # warm the instantiated graph / the step, and keep the GPU under load until nvidia-smi has delivered samples
     # (it needs a few hundred ms to start; a 0.2 ms region would otherwise end before the first one)
@@ -1102,7 +1122,12 @@ def measure(wl, ctx, K, W, args, want_e2e=True):
             for i in range(min(K, 8)):
                 wl.step(i)
         torch.cuda.synchronize()
-        if sampler is None or sampler.count() - n0 >= 3 or time.perf_counter() - t_warm > 1.5:
+        stop = sampler is None or sampler.count() - n0 >= 3 or time.perf_counter() - t_warm > 1.5
+        if world > 1:  # a step may contain a collective (the batch-wide control cost): every rank runs the same number
+            flag = torch.tensor([1.0 if (stop or rank != 0) else 0.0], device=dev)
+            dist.broadcast(flag, 0)
+            stop = flag.item() > 0
+        if stop:
             break
     _lib.call("emei_stats_reset", wl.stats.data_ptr(), torch.cuda.current_stream(dev).cuda_stream, launches=0)
     launches0 = _lib.launch_count
@@ -1130,12 +1155,21 @@ def measure(wl, ctx, K, W, args, want_e2e=True):
         launches = _lib.launch_count - launches0
     if world > 1:
         dist.barrier()
-    t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+    ms_outer = ev0.elapsed_time(ev1)
+    ms_region = ms_outer
+    if graph is not None and ev_in is not None:
+        try:
+            ms_inner = ev_in[0].elapsed_time(ev_in[1])
+            if 0.0 < ms_inner <= ms_outer:
+                ms_region = ms_inner
+        except RuntimeError:
+            pass
+    t = torch.tensor([ms_region, ms_outer], dtype=torch.float64, device=dev)
     units = torch.tensor([float(wl.units)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(units)
-    ms_total = float(t.item())
+    ms_total, ms_outer = float(t[0].item()), float(t[1].item())
     ms_per_step = ms_total / K
     value = float(units.item()) * K / (ms_total * 1e-3)
     graph = None
@@ -1168,6 +1202,26 @@ def measure(wl, ctx, K, W, args, want_e2e=True):
             "value": e2e_units * e2e_steps / (float(te.item()) * 1e-3), "unit": wl.unit,
             "h2d_bytes_per_step": wl.h2d, "d2h_bytes_per_step": wl.d2h, "steps": e2e_steps, "api": wl.e2e_api,
         }
+    e2e_light = None
+    if e2e is not None and hasattr(wl, "step_e2e_light"):
+        for i in range(getattr(wl, "e2e_warmup", 2)):
+            wl.step_e2e_light(i)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(e2e["steps"]):
+            wl.step_e2e_light(i)
+        e1.record()
+        torch.cuda.synchronize()
+        te = torch.tensor([max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        st = wl.env0._staging
+        e2e_light = {"value": float(units.item()) * e2e["steps"] / (float(te.item()) * 1e-3), "unit": wl.unit, "h2d_bytes_per_step": st.h2d_bytes,
+                     "d2h_bytes_per_step": st.d2h_bytes, "steps": e2e["steps"], "api": wl.e2e_light_api}
     t_clock1 = time.monotonic()
     if rank != 0:
         return None
@@ -1203,11 +1257,20 @@ def measure(wl, ctx, K, W, args, want_e2e=True):
         roofline["algorithmic_bytes_per_launch"] = bpu * wl.units
     cfg = full_config(type(wl), args, world)
     protocol = {
-        "launch": (f"K={K} steps captured in one CUDA graph (programmatic dependent launches), replayed once" if launch_mode == "graph"
+        "launch": (f"K={K} steps captured in one CUDA graph (programmatic dependent launches), replayed once; the two timing events are nodes "
+                   "of that graph, directly before the first step kernel and after the last" if launch_mode == "graph"
                    else f"K={K} step() calls launched back to back on one stream" + (" behind a spinning kernel (the device never waits for the host)" if wl.use_graph else ""))
                   + "; CUDA events on the launching stream",
         "parallelism": f"batch sharded over {world} rank(s), no data-path collective; NCCL all-reduce of the 2-double statistics at the end",
     }
+    if world > 1:
+        hb = getattr(args, "host_binding", None)
+        protocol["host_binding"] = (f"rank 0 bound to {len(hb)} CPUs local to its GPU's NUMA node" if hb else
+                                    "none: the host exposes one NUMA node / no per-GPU CPU locality")
+    if launch_mode == "graph":
+        protocol["ms_per_step_including_graph_launch"] = ms_outer / K
+        protocol["note"] = ("events recorded around graph.replay() also contain the graph's launch, a one-off per replay: "
+                            f"{(ms_outer - ms_total) * 1e3:.1f} us here")
     rec = {
         "metric": wl.metric, "value": value, "unit": wl.unit, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": wl.scaling, "vs_baseline": None,
@@ -1215,6 +1278,8 @@ def measure(wl, ctx, K, W, args, want_e2e=True):
         "e2e": e2e, "gpu_launches": launches,
         "clocks": sampler.summary(t_clock0, t_clock1) if sampler is not None else None,
     }
+    if e2e_light is not None:
+        rec["e2e_reward_done"] = e2e_light
     return rec
 
 
@@ -1239,7 +1304,15 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # NCCL's banner must not share stdout with the JSON line
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+
+        # a collective that cannot complete (a rank died) fails after two minutes instead of NCCL's ten
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=120))
+    # several ranks on one host: pin each to the CPUs next to its GPU before any pinned staging buffer is allocated
+    # (first touch places the pages on that NUMA node); a no-op where the host exposes a single node
+    from emei_b200.dist import bind_to_gpu_numa
+
+    args.host_binding = bind_to_gpu_numa(local) if world > 1 else None
     t_start = time.monotonic()
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler is not None:

@@ -26,6 +26,10 @@ constexpr uint32_t kChunk = 2 * kBlock;                       // envs per chunk
 constexpr int kTmaSmemBudget = 208 * 1024;                    // ring bytes (of 227 KB per SM)
 constexpr int kTmaMaxSlots = 24;
 constexpr uint32_t kChunkOutBytes = kChunk * 5;               // BULK: staged reward (4 B) + done (1 B) of a chunk
+// The first ring-full (up to 16 chunks x 2 bulk copies, ~1 000 instructions of one thread) is requested by the first
+// thread of the LAST consumer group: with 13.8 chunks per SM the groups own 4, 4, 3, 3 (or 4, 3, 3, 3) chunks, so the
+// last group's warps have a chunk's worth of slack while group 0's are on the critical path of the CTA.
+constexpr int kTmaProducerGroup = kTmaGroups - 1;
 
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -116,7 +120,11 @@ template <bool IP, int AK, int FR, bool HAS_OBS, int GROUPS = kTmaGroups, bool B
 __global__ void __launch_bounds__(GROUPS * kBlock, GROUPS == 4 ? 1 : 2)
     cartpole_step_f32_tma_kernel(const float4* state_in, float4* state_out, float4* obs_out,
                                  const void* __restrict__ action, float* __restrict__ reward, uint8_t* __restrict__ done,
-                                 double* stats, uint32_t n, int n_slots, int action_via_tma, const CartPoleF32Consts k) {
+                                 double* stats, uint32_t n, int n_slots, int flags, const CartPoleF32Consts k) {
+  // flags: bit 0 = the action array is 16-byte aligned (staged by TMA); bits 8.. = the consumer group whose first
+  // thread requests the first ring-full (kTmaProducerGroup)
+  const int action_via_tma = flags & 1;
+  const uint32_t producer_tid = static_cast<uint32_t>((flags >> 8) & 0xff) * kBlock;
   using f32::f2;
   using ActT = typename ActionStorage<AK>::type;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -178,7 +186,7 @@ __global__ void __launch_bounds__(GROUPS * kBlock, GROUPS == 4 ? 1 : 2)
     // The first ring-full is requested by ONE thread in consumption order (local chunks 0, 1, 2, ...): bulk copies
     // issued together share the bandwidth, so four producers starting at once made every chunk of the ring
     // complete late (10.8 us per step at 2^20 envs instead of 9.7); issued in order, chunk 0 lands first.
-    if (tid == 0) {
+    if (tid == producer_tid) {
       const uint32_t first = my_chunks < static_cast<uint32_t>(n_slots) ? my_chunks : static_cast<uint32_t>(n_slots);
       for (uint32_t j = 0; j < first; ++j) issue(j % GROUPS, j / GROUPS, (j % GROUPS) * spg + j / GROUPS);
     }
@@ -192,8 +200,9 @@ __global__ void __launch_bounds__(GROUPS * kBlock, GROUPS == 4 ? 1 : 2)
     uint32_t slot = slot0, phase = 0u;                      // slot / parity of the chunk consumed now
     uint32_t prev_slot = slot0, prev_phase = 0u;            // ... and of the previous iteration (the one to refill)
 
-    auto body = [&](auto full_tag) {
+    auto body = [&](auto full_tag, auto recycle_tag) {
       constexpr bool FULL = decltype(full_tag)::value;
+      constexpr bool RECYCLE = decltype(recycle_tag)::value;
       constexpr uint32_t kB = 32u;  // env B = env A + 32
       const bool live_a = FULL || i < n, live_b = FULL || i + kB < n;
       const bool act_tma = FULL && action_via_tma;  // partial tail: consumers read their actions directly
@@ -210,7 +219,7 @@ __global__ void __launch_bounds__(GROUPS * kBlock, GROUPS == 4 ? 1 : 2)
         if (live_a) aa = static_cast<float>(__ldg(act + i));
         if (live_b) ab = static_cast<float>(__ldg(act + i + kB));
       }
-      if (recycling) {
+      if constexpr (RECYCLE) {
         __syncwarp();
         if ((t & 31u) == 0) mbar_arrive_u32(empty_u32 + slot * 8u);  // this warp's reads of the slot are done
       }
@@ -313,21 +322,34 @@ __global__ void __launch_bounds__(GROUPS * kBlock, GROUPS == 4 ? 1 : 2)
       }
     };
 
-    for (uint32_t m = 0; m < my_g; ++m) {
-      if (recycling && t == 0 && m >= 1 && m - 1 + spg < my_g) {  // refill the slot read one iteration ago
-        mbar_wait(&empty[prev_slot], prev_phase);
-        issue(g, m - 1 + spg, prev_slot);
+    if (!recycling) {
+      // the whole share of this group is in the ring (BASELINE configs[1]: 2^20 envs): no refill logic, no empty
+      // barriers, one slot per chunk -- the loop carries the env index and the slot only
+      for (uint32_t m = 0; m < my_g; ++m) {
+        if (i - tw + kChunk <= n)
+          body(std::true_type{}, std::false_type{});
+        else
+          body(std::false_type{}, std::false_type{});
+        i += i_step;
+        ++slot;
       }
-      if (i - tw + kChunk <= n)
-        body(std::true_type{});
-      else
-        body(std::false_type{});
-      i += i_step;
-      prev_slot = slot;
-      prev_phase = phase;
-      if (++slot == slot0 + spg) {
-        slot = slot0;
-        phase ^= 1u;
+    } else {
+      for (uint32_t m = 0; m < my_g; ++m) {
+        if (t == 0 && m >= 1 && m - 1 + spg < my_g) {  // refill the slot read one iteration ago
+          mbar_wait(&empty[prev_slot], prev_phase);
+          issue(g, m - 1 + spg, prev_slot);
+        }
+        if (i - tw + kChunk <= n)
+          body(std::true_type{}, std::true_type{});
+        else
+          body(std::false_type{}, std::true_type{});
+        i += i_step;
+        prev_slot = slot;
+        prev_phase = phase;
+        if (++slot == slot0 + spg) {
+          slot = slot0;
+          phase ^= 1u;
+        }
       }
     }
   }
@@ -474,7 +496,7 @@ inline void launch_cartpole_f32_tma(int ak, cudaStream_t s, const float* state_i
     float4* out4 = reinterpret_cast<float4*>(state_out) + off;
     float4* obs4 = obs_out ? reinterpret_cast<float4*>(obs_out) + off : nullptr;
     const void* act = static_cast<const char*>(action) + off * action_bytes;
-    const int act_tma = (reinterpret_cast<uintptr_t>(act) & 15u) == 0 ? 1 : 0;
+    const int act_tma = ((reinterpret_cast<uintptr_t>(act) & 15u) == 0 ? 1 : 0) | (kTmaProducerGroup << 8);
     switch (ak) {
 #define EMEI_AK(A)                                                                                                       \
   case A:                                                                                                                \

@@ -336,3 +336,19 @@ def test_step_host_ranges_are_aligned_partitions():
             assert r[0][0] == 0 and r[-1][1] == n
             assert all(a[1] == b[0] for a, b in zip(r, r[1:])) and all(hi > lo for lo, hi in r)
             assert all(lo % 16 == 0 for lo, _ in r)
+
+
+def test_numa_binding_helpers_are_safe_without_topology():
+    """emei_b200.dist.bind_to_gpu_numa: parses sysfs CPU lists, and changes nothing where there is no GPU / no
+    per-GPU locality (this container)."""
+    import os
+
+    from emei_b200 import dist as D
+
+    assert sorted(D._parse_cpulist("0-3,8,10-11")) == [0, 1, 2, 3, 8, 10, 11]
+    assert D._parse_cpulist("") == set()
+    before = os.sched_getaffinity(0)
+    assert D.bind_to_gpu_numa(0) is None or isinstance(D.bind_to_gpu_numa(0), list)
+    if not __import__("torch").cuda.is_available():
+        assert D.gpu_numa_info(0) == {"pci": None, "numa_node": None, "local_cpulist": None}
+        assert os.sched_getaffinity(0) == before

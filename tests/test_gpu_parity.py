@@ -357,7 +357,7 @@ def test_c1_protocol_ip_f32_teacher_forced_200_steps(kind, fr):
     dth = np.abs((o[:, 1] - ref_obs[:, 1] + np.pi) % (2 * np.pi) - np.pi)  # wrapped angle: compare on the circle
     assert np.all(dth <= 1e-6 + 1e-5 * np.abs(ref_state[:, 1]))
     assert np.all((o[:, 1] >= -np.pi - 1e-6) & (o[:, 1] <= np.pi + 1e-6))
-    assert within32(o[:, [0, 2, 3]], ref_obs[:, [0, 2, 3]]).all()
+    assert np.all(np.abs(o[:, [0, 2, 3]] - ref_obs[:, [0, 2, 3]]) <= tol[:, [0, 2, 3]])
     assert within32(rew.cpu().numpy(), O.ip_reward(kind, ref_obs)).all()
     ref_done = O.ip_terminal(kind, ref_obs, p)
     cy = np.cos(ref_obs[:, 1])
@@ -1389,8 +1389,7 @@ def test_ip_obs_noise_vs_oracle_and_philox_mirror(dtype, fr):
     half.step(act[n // 2 :])
     full.step(act)
     assert torch.equal(half.state, full.state[n // 2 :])
-    with pytest.raises(NotImplementedError):
-        full.rollout(4)
+    # (noise inside fused rollouts: test_rollout_ref_equals_step_calls)
     # the host path draws the same noise (ranges keyed by their global env ids, no graph replay with a moving counter)
     h = E.make(IP[kind], freq_rate=fr, num_envs=n, dtype=dtype, obs_noise_params=(0.01, 0.03))
     g = E.make(IP[kind], freq_rate=fr, num_envs=n, dtype=dtype, obs_noise_params=(0.01, 0.03))

@@ -136,7 +136,7 @@ float time_stream(F launch, int K, cudaStream_t s, int reps = 5) {
 
 // shape variants of the shipped kernel: GROUPS consumer groups per CTA, BULK stores, CTAs per SM, ring budget
 template <int GROUPS, bool BULK>
-void run_tma2(const char* name, Ring& R, uint32_t n, int K, cudaStream_t s, int ctas_per_sm, int budget_kb) {
+void run_tma2(const char* name, Ring& R, uint32_t n, int K, cudaStream_t s, int ctas_per_sm, int budget_kb, int producer_group = 0) {
   SKIP(name);
   emei_cartpole_params p = {};
   p.gravity = 9.8; p.mass_pole = 0.1; p.total_mass = 1.1; p.length = 0.5; p.pole_mass_length = 0.05; p.force_mag = 10.0;
@@ -156,7 +156,7 @@ void run_tma2(const char* name, Ring& R, uint32_t n, int K, cudaStream_t s, int 
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   auto launch = [&](int i) {
     int j = i % ring;
-    launch_pdl_smem(kern, grid, GROUPS * kBlock, smem, s, (const float4*)R.in[j], (float4*)R.out[j], (float4*)nullptr, (const void*)R.act[j], R.rew[j], R.done[j], stats, n, n_slots, 1, k);
+    launch_pdl_smem(kern, grid, GROUPS * kBlock, smem, s, (const float4*)R.in[j], (float4*)R.out[j], (float4*)nullptr, (const void*)R.act[j], R.rew[j], R.done[j], stats, n, n_slots, 1 | (producer_group << 8), k);
   };
   float us = time_graph(launch, K, s);
   CK(cudaGetLastError());
@@ -267,7 +267,10 @@ int main(int argc, char** argv) {
   run_tma<4>("TMA packed fr4 (shipped)", R, n, K, s);
   run_tma<4>("TMA packed fr4 slots<=8", R, n, K, s, 8);
   // ---- round 2: shape variants (GROUPS per CTA, bulk stores, CTAs per SM, ring budget in KB)
-  run_tma2<4, false>("r2 G4 direct stores (shipped shape)", R, n, K, s, 1, 208);
+  run_tma2<4, false>("r2 G4 direct stores, producer = group 0", R, n, K, s, 1, 208, 0);
+  run_tma2<4, false>("r2 G4 direct stores, producer = group 1", R, n, K, s, 1, 208, 1);
+  run_tma2<4, false>("r2 G4 direct stores, producer = group 2", R, n, K, s, 1, 208, 2);
+  run_tma2<4, false>("r2 G4 direct stores, producer = group 3 (shipped)", R, n, K, s, 1, 208, 3);
   run_tma2<4, true>("r2 G4 BULK stores", R, n, K, s, 1, 216);
   run_tma2<2, false>("r2 G2 half-SM, 1 CTA/SM/kernel, 10 slots", R, n, K, s, 1, 104);
   run_tma2<2, false>("r2 G2 half-SM, 1 CTA/SM/kernel, 8 slots", R, n, K, s, 1, 84);
