@@ -732,6 +732,54 @@ class ScoringSweep(Workload):
         return 2 * cls.n_half * world
 
 
+class ScoringSweepSeq(ScoringSweep):
+    """C5 with the imagined rollouts held as trajectory tensors obs_seq [17, 2^21, D] per family (the layout an MBRL
+    scorer produces them in): get_batch_reward_terminal_seq reads every observation row once."""
+
+    key = "c5_seq"
+    title = ScoringSweep.title.replace("reward+terminal", "reward+terminal on trajectory tensors obs_seq[17, 2^21, D]")
+    kernel = "emei::reward_terminal_seq_kernel<float, HALFCHEETAH> (dominant), HOPPER, sumsq, snapshot_copy"
+    T, n_traj = 16, 1 << 21
+    alg_bytes = ((65 + 48 / 16) + (101 + 72 / 16)) / 2 + 64
+
+    def setup(self):
+        import torch
+
+        import emei_b200 as E
+
+        self.units = 2 * self.n_half
+        assert self.T * self.n_traj == self.n_half
+        self.hop = E.make("HopperRunning-v0", terminate_when_unhealthy=False, dtype=torch.float32, device=self.dev)
+        self.chee = E.make("HalfCheetahRunning-v0", dtype=torch.float32, device=self.dev)
+        self.cp = E.make("CartPoleSwingUp-v0", num_envs=self.n_env, dtype=torch.float32, device=self.dev, copy_outputs=False)
+        self.cp.reset(seed=1005)
+        g = torch.Generator(device=self.dev)
+        g.manual_seed(1005 + 31 * self.rank)
+        self.data = []
+        for d, da in ((12, 3), (18, 6)):
+            seq = torch.randn((self.T + 1, self.n_traj, d), device=self.dev, generator=g)
+            if d == 12:
+                seq[:, :, 1] += 1.25
+            self.data.append((seq, torch.rand((self.T, self.n_traj, da), device=self.dev, generator=g) * 2 - 1))
+        self.stats = self.hop.stats
+
+    def step(self, i):
+        self.cp.freeze()
+        self.o1 = self.hop.get_batch_reward_terminal_seq(*self.data[0])
+        self.o2 = self.chee.get_batch_reward_terminal_seq(*self.data[1])
+        self.cp.unfreeze()
+
+    def setup_e2e(self):
+        return Workload.setup_e2e(self)
+
+    @classmethod
+    def config(cls, args, world):
+        c = ScoringSweep.config.__func__(cls, args, world)
+        c["layout"] = f"obs_seq [T+1={cls.T + 1}, n={cls.n_traj}, D], action [T, n, A] per family"
+        c["l2_policy"] = "inputs larger than L2 (8 GB per sweep)"
+        return c
+
+
 class CartPoleRollout(Workload):
     """the collection loop (zoo/util.py:33-93) as ONE launch per `horizon` env-steps: state,
     TimeLimit counter and episode return in registers, in-kernel auto-reset and uniform random policy.  No
@@ -878,7 +926,8 @@ class ChargedBallRollout(Workload):
 
 
 WORKLOADS = {w.key: w for w in (IPStep, CartPoleStep, CartPoleStepLarge, I2PStep, HopperScoring, HalfCheetahScoring, HopperSeqScoring,
-                                HalfCheetahSeqScoring, ChargedBall, ScoringSweep, CartPoleRollout, CartPoleRolloutRecord, ChargedBallRollout)}
+                                HalfCheetahSeqScoring, ChargedBall, ScoringSweep, ScoringSweepSeq, CartPoleRollout, CartPoleRolloutRecord,
+                                ChargedBallRollout)}
 
 
 def workload_name(W, args):
@@ -1243,7 +1292,8 @@ def measure(wl, ctx, K, W, args, want_e2e=True):
         pk = mm["peaks"]["sfu_ops_per_s" if binding == "sfu" else "fp32_lane_ops_per_s"]
         roofline = {
             "bound": "math", "achieved": ops * wl.units / step_s / 1e12, "peak": pk / 1e12, "unit": f"T {binding} op/s (algorithmic)",
-            "frac": mm["t_math_us"] * 1e-6 / step_s, "traffic": None, "kernel": wl.kernel_name(), "kernel_ms_per_launch": ms_per_step,
+            "frac": mm["frac_of_slower_bound"], "traffic": None, "kernel": wl.kernel_name(), "kernel_ms_per_launch": ms_per_step,
+            "frac_of_math_bound": mm["t_math_us"] * 1e-6 / step_s,
             "binding_unit": binding, "math": mm,
             "hbm": {"algorithmic_bytes_per_unit": bpu, "achieved_gbs": achieved, "frac_of_hbm_peak": achieved / peak},
             "note": "duration = CUDA-event time per launch; operations = SURVEY 8(d)'s algorithmic counts per env-step x env-steps",
@@ -1284,8 +1334,8 @@ def measure(wl, ctx, K, W, args, want_e2e=True):
 
 
 SECONDARY_N1 = [("c1", "f32"), ("c2_f64", "f64"), ("c3_hopper", "f32"), ("c3_halfcheetah", "f32"), ("c3_hopper_seq", "f32"),
-                ("c3_halfcheetah_seq", "f32"), ("c4", "f32"), ("c4_rollout", "f32"), ("c5", "f32")]
-SECONDARY_MULTI = [("c4", "f32"), ("c4_rollout", "f32"), ("c5", "f32")]
+                ("c3_halfcheetah_seq", "f32"), ("c4", "f32"), ("c4_rollout", "f32"), ("c5", "f32"), ("c5_seq", "f32")]
+SECONDARY_MULTI = [("c4", "f32"), ("c4_rollout", "f32"), ("c5", "f32"), ("c5_seq", "f32")]
 
 
 def run_ours(args):

@@ -160,8 +160,9 @@ void run_tma2(const char* name, Ring& R, uint32_t n, int K, cudaStream_t s, int 
   };
   float us = time_graph(launch, K, s);
   CK(cudaGetLastError());
-  float us20g = time_graph(launch, 20, s, 9);
-  float us20s = time_stream(launch, 20, s, 9);
+  const int reps20 = getenv("KBENCH_REPS") ? atoi(getenv("KBENCH_REPS")) : 9;  // 1: a single shot, like bench.py's timed region
+  float us20g = time_graph(launch, 20, s, reps20);
+  float us20s = time_stream(launch, 20, s, reps20);
   CK(cudaGetLastError());
   int occ = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, GROUPS * kBlock, smem);
   printf("%-52s grid=%4d thr=%4d slots=%2d smem=%6zu occ=%d  graph K=%d: %6.2f us  %5.0f GB/s | K=20 graph %6.2f us, K=20 stream launches %6.2f us\n",
