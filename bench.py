@@ -948,11 +948,12 @@ def cpu_literal(workload):
     the BUILD container by scripts/time_reference_literal.py (the GPU box has no reference tree), carried as a constant."""
     try:
         d = json.load(open(os.path.join(ROOT, "profiles", "cpu_literal.json")))
-        w = d["workloads"].get({"c1": "c1_cartpole_counterpart"}.get(workload, workload))
+        w = d["workloads"].get({"c1": "c1_cartpole_counterpart", "c3_hopper_seq": "c3_hopper", "c3_halfcheetah_seq": "c3_halfcheetah"}.get(workload, workload))
         if w is None:
             return None
-        return {"one_core": w["one_core"], "all_cores": w["all_cores"], "processes": w["processes"], "unit": d["unit"],
-                "env": w["env"], "freq_rate": w["freq_rate"], "kind": "reference-literal, measured in the build container (NOT on this box)",
+        return {"one_core": w["one_core"], "all_cores": w["all_cores"], "processes": w["processes"],
+                "unit": d["unit"] if "freq_rate" in w else d.get("unit_scoring", "transitions/s"),
+                "env": w["env"], "freq_rate": w.get("freq_rate"), "kind": "reference-literal, measured in the build container (NOT on this box)",
                 "provenance": f"{d['script']} on {d['cpu']} ({d['cores_available']} cores), {d['when']}: {d['what']}"}
     except Exception:
         return None
@@ -1417,9 +1418,13 @@ def run_ours(args):
                     raise
             w2.teardown()
             del w2
+            if rank == 0 and rec is not None and "error" not in rec:
+                lit = cpu_literal(key)
+                if lit is not None:
+                    rec["cpu_baseline_literal"] = lit
             if rank == 0 and rec is not None:
                 sec[name] = {k: rec[k] for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "scaling", "dtype", "config", "roofline",
-                                                 "e2e", "gpu_launches", "clocks") if k in rec} if "error" not in rec else rec
+                                                 "e2e", "e2e_reward_done", "gpu_launches", "clocks", "cpu_baseline_literal") if k in rec} if "error" not in rec else rec
         if rank == 0:
             line["secondary"] = sec
     if rank == 0:

@@ -85,6 +85,26 @@ def main():
         rn = rate(kind, fr, 15000, cores)
         out["workloads"][key] = {"env": kind, "freq_rate": fr, "one_core": r1, "all_cores": rn, "processes": cores}
         print(key, f"1 core {r1:.0f} env-steps/s, {cores} processes {rn:.0f} env-steps/s")
+    # the reference's own (already vectorised) get_batch_reward + get_batch_terminal on float64 numpy arrays, one process
+    # (hopper.py:79-106, half_cheetah.py:59-67 executed from /root/reference through the MuJoCo-less shell of ref_loader)
+    out["unit_scoring"] = "transitions/s"
+    for key, name, d, da, kw in (("c3_hopper", "hopper", 12, 3, dict(terminate_when_unhealthy=False)), ("c3_halfcheetah", "half_cheetah", 18, 6, {})):
+        env = RL.make_mujoco_shell(name, **kw)
+        rng = np.random.default_rng(3)
+        n = 1 << 20
+        obs = rng.standard_normal((n, d))
+        pre = obs + 0.01 * rng.standard_normal((n, d))
+        act = rng.uniform(-1, 1, size=(n, da))
+        env.get_batch_reward(obs, pre, act), env.get_batch_terminal(obs, pre, act)
+        t0 = time.perf_counter()
+        reps = 5
+        for _ in range(reps):
+            env.get_batch_reward(obs, pre, act)
+            env.get_batch_terminal(obs, pre, act)
+        r1 = n * reps / (time.perf_counter() - t0)
+        out["workloads"][key] = {"env": name, "one_core": r1, "all_cores": None, "processes": 1, "batch": n,
+                                 "note": "get_batch_reward + get_batch_terminal of the unmodified reference class, float64 numpy, 2^20 transitions per call"}
+        print(key, f"1 process {r1:.0f} transitions/s")
     path = os.path.join(ROOT, "profiles", "cpu_literal.json")
     json.dump(out, open(path, "w"), indent=1)
     print("wrote", path)

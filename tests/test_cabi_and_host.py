@@ -352,3 +352,40 @@ def test_numa_binding_helpers_are_safe_without_topology():
     if not __import__("torch").cuda.is_available():
         assert D.gpu_numa_info(0) == {"pci": None, "numa_node": None, "local_cpulist": None}
         assert os.sched_getaffinity(0) == before
+
+
+def test_round2_entry_points_validate_arguments_without_a_gpu():
+    """The entry points added in round 2 reject bad arguments with EMEI_ERR_* codes before any CUDA call, and treat
+    empty work as a valid no-op (include/emei_b200.h conventions)."""
+    import ctypes
+
+    from emei_b200 import _lib
+
+    L = _lib.lib
+    sp = _lib.ScoringParams()
+    sp.family, sp.dt = _lib.HOPPER, 0.008
+    for sfx in ("_f32", "_f64"):
+        seq = getattr(L, "emei_reward_terminal_seq" + sfx)
+        assert seq(None, None, None, None, None, 0, 5, ctypes.byref(sp), None) == 0          # no envs
+        assert seq(None, None, None, None, None, 7, 0, ctypes.byref(sp), None) == 0          # no steps
+        assert seq(None, None, None, None, None, -1, 5, ctypes.byref(sp), None) == -4        # EMEI_ERR_BAD_SIZE
+        assert seq(None, None, None, None, None, 8, 5, None, None) == -1                     # EMEI_ERR_NULL_POINTER (params)
+        assert seq(None, None, None, None, None, 8, 5, ctypes.byref(sp), None) == -1         # obs_seq missing
+        bad = _lib.ScoringParams()
+        bad.family = 99
+        assert seq(None, None, None, None, None, 8, 5, ctypes.byref(bad), None) == -2        # EMEI_ERR_BAD_VARIANT
+        cp, rp, z = _lib.CartPoleParams(), _lib.RolloutParams(), _lib.NoiseParams()
+        cp.freq_rate, cp.dt, cp.variant = 1, 0.02, _lib.CARTPOLE_SWINGUP
+        ro = getattr(L, "emei_cartpole_rollout_ref" + sfx)
+        args = [None] * 12
+        assert ro(*args, 0, ctypes.byref(cp), ctypes.byref(rp), None, None) == -1            # episode buffers missing
+        assert ro(*args, -3, ctypes.byref(cp), ctypes.byref(rp), None, None) == -4
+        assert ro(*args, 4, ctypes.byref(cp), ctypes.byref(rp), ctypes.byref(z), None) == -2  # noise exists for the IP variants only
+        ip = _lib.I2PParams()
+        i2 = getattr(L, "emei_i2p_rollout" + sfx)
+        Arr = ctypes.c_double * 6
+        assert i2(*args, 4, ctypes.byref(ip), ctypes.byref(rp), Arr(), Arr(), None, None) == -2   # variant 0 is not an I2P variant
+        assert i2(*args, 4, ctypes.byref(ip), ctypes.byref(rp), None, None, None, None) == -1
+        cb = _lib.ChargedBallParams()
+        cr = getattr(L, "emei_charged_ball_rollout_ref" + sfx)
+        assert cr(*([None] * 14), 4, ctypes.byref(cb), ctypes.byref(rp), None) == -6         # EMEI_ERR_BAD_PARAM (freq_rate 0)
