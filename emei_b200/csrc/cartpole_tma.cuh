@@ -109,6 +109,21 @@ __device__ __forceinline__ void sts128(uint32_t addr, const float4& v) {
 __device__ __forceinline__ void sts32(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
 __device__ __forceinline__ void sts8(uint32_t addr, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
 
+#ifdef EMEI_TMA_TRACE
+// development only (tools/kbench -DEMEI_TMA_TRACE): per (CTA, group) timestamps of the chunk pipeline
+__device__ unsigned long long* g_tma_trace = nullptr;  // [gridDim.x][GROUPS][64]
+__device__ __forceinline__ unsigned long long tma_now() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define EMEI_TRACE(slot_idx)                                                                                     \
+  if (g_tma_trace != nullptr && t == 0 && (slot_idx) < 64)                                                       \
+  g_tma_trace[(static_cast<size_t>(blockIdx.x) * GROUPS + g) * 64 + (slot_idx)] = tma_now()
+#else
+#define EMEI_TRACE(slot_idx)
+#endif
+
 // GROUPS consumer groups of 256 threads per CTA (4: one CTA fills an SM; 2: half an SM, so that the CTA of the NEXT
 // step kernel -- launched early by programmatic dependent launch -- can already be resident, initialised and
 // parked in griddepcontrol.wait while this one computes).  BULK: a warp stages its 64 envs' outputs in shared memory
@@ -167,6 +182,14 @@ __global__ void __launch_bounds__(GROUPS * kBlock, GROUPS == 4 ? 1 : 2)
     // env index and the slot / phase pair.  The body is compiled twice: FULL (every chunk but possibly the last
     // of the batch: no per-lane predicates) and the ragged tail.
     const uint32_t g = tid / kBlock, t = tid % kBlock;
+    EMEI_TRACE(0);  // after griddepcontrol.wait
+#ifdef EMEI_TMA_TRACE
+    if (g_tma_trace != nullptr && t == 0) {
+      unsigned smid;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      g_tma_trace[(static_cast<size_t>(blockIdx.x) * GROUPS + g) * 64 + 63] = smid;
+    }
+#endif
     const uint32_t flip = ip_flip(IP, k.variant);
     const uint32_t spg = static_cast<uint32_t>(n_slots) / GROUPS;                  // slots per group (n_slots % GROUPS == 0)
     const uint32_t my_g = my_chunks > g ? (my_chunks - g + GROUPS - 1) / GROUPS : 0;  // this group's chunks
@@ -200,6 +223,7 @@ __global__ void __launch_bounds__(GROUPS * kBlock, GROUPS == 4 ? 1 : 2)
     uint32_t slot = slot0, phase = 0u;                      // slot / parity of the chunk consumed now
     uint32_t prev_slot = slot0, prev_phase = 0u;            // ... and of the previous iteration (the one to refill)
 
+    [[maybe_unused]] uint32_t trace_m = 0;
     auto body = [&](auto full_tag, auto recycle_tag) {
       constexpr bool FULL = decltype(full_tag)::value;
       constexpr bool RECYCLE = decltype(recycle_tag)::value;
@@ -207,6 +231,7 @@ __global__ void __launch_bounds__(GROUPS * kBlock, GROUPS == 4 ? 1 : 2)
       const bool live_a = FULL || i < n, live_b = FULL || i + kB < n;
       const bool act_tma = FULL && action_via_tma;  // partial tail: consumers read their actions directly
       mbar_wait_u32(full_u32 + slot * 8u, phase);
+      EMEI_TRACE(2 + 2 * trace_m);  // this chunk's bytes have landed
       const uint32_t sl = state_u32 + slot * (kChunk * 16u);
       float4 ya = live_a ? lds128(sl) : make_float4(0.f, 0.f, 0.f, 0.f);
       float4 yb = live_b ? lds128(sl + kB * 16u) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -320,6 +345,8 @@ __global__ void __launch_bounds__(GROUPS * kBlock, GROUPS == 4 ? 1 : 2)
           d_cnt += nd_b ? 0u : 1u;
         }
       }
+      EMEI_TRACE(3 + 2 * trace_m);  // this chunk's stores are issued
+      ++trace_m;
     };
 
     if (!recycling) {
@@ -353,6 +380,9 @@ __global__ void __launch_bounds__(GROUPS * kBlock, GROUPS == 4 ? 1 : 2)
       }
     }
   }
+#ifdef EMEI_TMA_TRACE
+  if (g_tma_trace != nullptr && (tid % kBlock) == 0) g_tma_trace[(static_cast<size_t>(blockIdx.x) * GROUPS + tid / kBlock) * 64 + 1] = tma_now();  // group done
+#endif
   if constexpr (BULK) {  // the staged outputs must have been read before the CTA's shared memory goes away
     if ((tid & 31u) == 0) tma_store_wait_read0();
   }

@@ -5,6 +5,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
+#include <array>
+#include <algorithm>
 #include "../../emei_b200/csrc/cartpole_tma.cuh"
 
 using namespace emei;
@@ -240,6 +242,79 @@ void run_stream(const char* name, Ring& R, uint32_t n, int K, cudaStream_t s) {
   printf("%-44s grid=%5d  %7.2f us/launch  %6.1f Genv-steps/s  %6.0f GB/s (41 B/env)\n", name, grid, us, n / us * 1e-3, 41.0 * n / us * 1e-3);
 }
 
+#ifdef EMEI_TMA_TRACE
+// one steady-state launch's chunk pipeline: when each group's chunks landed and when their stores were issued
+void run_trace(Ring& R, uint32_t n, cudaStream_t s) {
+  emei_cartpole_params p = {};
+  p.gravity = 9.8; p.mass_pole = 0.1; p.total_mass = 1.1; p.length = 0.5; p.pole_mass_length = 0.05; p.force_mag = 10.0;
+  p.x_threshold = 5.0; p.theta_threshold = 0.2; p.dt = 0.02; p.freq_rate = 4; p.variant = EMEI_CARTPOLE_SWINGUP;
+  p.action_kind = EMEI_ACTION_CONTINUOUS_F32;
+  CartPoleF32Consts k = make_cartpole_f32_consts(p);
+  const int64_t chunks = (n + kChunk - 1) / kChunk;
+  const int grid = (int)(chunks < kNumSMs ? chunks : kNumSMs);
+  int n_slots; size_t smem;
+  tma_ring_shape(4, (chunks + grid - 1) / grid, &n_slots, &smem);
+  auto kern = cartpole_step_f32_tma_kernel<false, EMEI_ACTION_CONTINUOUS_F32, 4, false>;
+  CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  double* stats; CK(cudaMalloc(&stats, 16)); CK(cudaMemset(stats, 0, 16));
+  const size_t words = (size_t)grid * 4 * 64;
+  unsigned long long* d_trace; CK(cudaMalloc(&d_trace, words * 8)); CK(cudaMemset(d_trace, 0, words * 8));
+  unsigned long long* null_ptr = nullptr;
+  const int ring = (int)R.in.size();
+  auto launch = [&](int i) {
+    int j = i % ring;
+    launch_pdl_smem(kern, grid, kTmaThreads, smem, s, (const float4*)R.in[j], (float4*)R.out[j], (float4*)nullptr, (const void*)R.act[j], R.rew[j], R.done[j], stats, n, n_slots, 1 | (kTmaProducerGroup << 8), k);
+  };
+  for (int i = 0; i < 40; ++i) launch(i);  // steady state, untraced
+  CK(cudaStreamSynchronize(s));
+  CK(cudaMemcpyToSymbol(g_tma_trace, &d_trace, sizeof(d_trace)));
+  for (int i = 40; i < 40 + (getenv("TRACE_LAUNCHES") ? atoi(getenv("TRACE_LAUNCHES")) : 3); ++i) launch(i);  // back-to-back launches overwrite each other's trace: the LAST one stays
+  CK(cudaStreamSynchronize(s));
+  CK(cudaMemcpyToSymbol(g_tma_trace, &null_ptr, sizeof(null_ptr)));
+  std::vector<unsigned long long> h(words);
+  CK(cudaMemcpy(h.data(), d_trace, words * 8, cudaMemcpyDeviceToHost));
+  unsigned long long t0 = ~0ull;
+  for (size_t i = 0; i < words; i += 64) if (h[i] && h[i] < t0) t0 = h[i];
+  printf("trace of one steady-state launch (ns after the earliest group passed griddepcontrol.wait); per group: start | chunk landed -> stores issued ... | done\n");
+  for (int cta : {0, 1, 73, 74, 123, 124, 146, 147}) {
+    for (int g = 0; g < 4; ++g) {
+      const unsigned long long* e = &h[((size_t)cta * 4 + g) * 64];
+      printf("cta %3d g%d  start %5lld |", cta, g, (long long)(e[0] - t0));
+      for (int m = 0; m < 6 && e[2 + 2 * m]; ++m) printf(" %5lld->%5lld", (long long)(e[2 + 2 * m] - t0), (long long)(e[3 + 2 * m] - t0));
+      printf(" | done %5lld\n", (long long)(e[1] - t0));
+    }
+  }
+  // distribution over all CTAs: when the first / last chunk landed, when the group finished
+  double first_land = 0, last_land = 0, done = 0; long long max_done = 0; int cnt = 0;
+  for (int cta = 0; cta < grid; ++cta) for (int g = 0; g < 4; ++g) {
+    const unsigned long long* e = &h[((size_t)cta * 4 + g) * 64];
+    if (!e[2]) continue;
+    int m = 0; while (m < 6 && e[2 + 2 * (m + 1)]) ++m;
+    first_land += (double)(e[2] - t0); last_land += (double)(e[2 + 2 * m] - t0); done += (double)(e[1] - t0);
+    if ((long long)(e[1] - t0) > max_done) max_done = (long long)(e[1] - t0);
+    ++cnt;
+  }
+  printf("mean over %d groups: first chunk landed %.0f ns, last chunk landed %.0f ns, group done %.0f ns; latest group done %lld ns\n", cnt, first_land / cnt, last_land / cnt, done / cnt, max_done);
+  // per CTA: SM id, chunks, first landing, last landing, done (max over groups), sorted by done
+  std::vector<std::array<long long, 6>> rows;
+  for (int cta = 0; cta < grid; ++cta) {
+    long long fl = 1LL << 60, ll = 0, dn = 0; int nch = 0;
+    for (int g = 0; g < 4; ++g) {
+      const unsigned long long* e = &h[((size_t)cta * 4 + g) * 64];
+      for (int m = 0; m < 6 && e[2 + 2 * m]; ++m) { long long v = (long long)(e[2 + 2 * m] - t0); if (v < fl) fl = v; if (v > ll) ll = v; ++nch; }
+      if ((long long)(e[1] - t0) > dn) dn = (long long)(e[1] - t0);
+    }
+    rows.push_back({dn, (long long)cta, (long long)h[((size_t)cta * 4) * 64 + 63], (long long)nch, fl, ll});
+  }
+  std::sort(rows.begin(), rows.end());
+  printf("per CTA sorted by completion: done_ns cta smid chunks first_landed last_landed\n");
+  for (size_t i = 0; i < rows.size(); ++i)
+    if (i < 6 || i + 24 >= rows.size() || i % 16 == 0)
+      printf("  %6lld  cta %3lld  sm %3lld  chunks %2lld  first %5lld  last %5lld\n", rows[i][0], rows[i][1], rows[i][2], rows[i][3], rows[i][4], rows[i][5]);
+  cudaFree(stats); cudaFree(d_trace);
+}
+#endif
+
 int main(int argc, char** argv) {
   const uint32_t n = argc > 1 ? (uint32_t)atol(argv[1]) : (1u << 20);
   const int ring = argc > 2 ? atoi(argv[2]) : 8;
@@ -260,6 +335,10 @@ int main(int argc, char** argv) {
     R.in.push_back(a); R.out.push_back(b); R.act.push_back(c); R.rew.push_back(d); R.done.push_back(e);
   }
   printf("n=%u ring=%d K=%d\n", n, ring, K);
+#ifdef EMEI_TMA_TRACE
+  run_trace(R, n, s);
+  return 0;
+#endif
   run_stream<8, true>("stream minb8 pdl", R, n, K, s);
   run_compute<4, 4, true>("compute-only scalar fr4 minb4 sincos/sub-step", R, n, K, s);
   run_compute<4, 4, false>("compute-only scalar fr4 minb4 angle-addition", R, n, K, s);
