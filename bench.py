@@ -788,10 +788,13 @@ class CartPoleRollout(Workload):
     key, metric, unit = "rollout", "env_steps_per_sec", "env-steps/s"
     title = "ContinuousCartPoleSwingUp fused rollout, 2^20 envs/GPU x horizon steps per launch, freq_rate=4, in-kernel random policy + TimeLimit(1000) + auto-reset (SURVEY 8f rank 1)"
     kernel = "emei::rollout_f32_kernel<CartPoleDyn<IP=0, AK=f32, FR=4>, RECORD=0>"
+    kernel_f64 = "emei::rollout_ref_kernel<RefCartPole<double, IP=0>> (the float64 step's own arithmetic, one env per thread)"
     env_id, n_envs, freq_rate = "ContinuousCartPoleSwingUp-v0", 1 << 20, 4
     use_graph, bound = False, "math"
     record = False
-    alg_fp_ops, alg_sfu_ops = CartPoleStep.alg_fp_ops, CartPoleStep.alg_sfu_ops
+    supports_f64 = True
+    state_bytes = 16
+    alg_fp_ops, alg_sfu_ops, alg_fp64_ops = CartPoleStep.alg_fp_ops, CartPoleStep.alg_sfu_ops, CartPoleStep.alg_fp64_ops
     inst_per_unit = 247.1  # thread-level SASS instructions per env-step incl. divergent in-kernel resets (ncu, profiles/r01_launches_rollout*.csv)
     cpu_kind = "c2"
     e2e_max_steps = 5
@@ -808,11 +811,12 @@ class CartPoleRollout(Workload):
         self.T = self._horizon(self.args)
         self.units = self.n_envs * self.T
         self.env = E.make(self.env_id, freq_rate=self.freq_rate, real_time_scale=DT, num_envs=self.n_envs,
-                          dtype=torch.float32, device=self.dev, env_offset=self.rank * self.n_envs)
+                          dtype=_tdtype(self.args), device=self.dev, env_offset=self.rank * self.n_envs)
         self.env.reset(seed=1006)
         self.stats = self.env.stats
-        # state 16 + 3 counters 12, read and written once per launch; records (if any) per env-step
-        self.alg_bytes = 2 * 28 / self.T + (42 if self.record else 0)
+        # state + 3 counters 12, read and written once per launch; records (if any) per env-step
+        sb = self.state_bytes * (2 if self.f64 else 1)
+        self.alg_bytes = self.alg_bytes_f64 = 2 * (sb + 12) / self.T + (42 if self.record else 0)
 
     def step(self, i):
         self.out = self.env.rollout(self.T, record=self.record)
@@ -843,6 +847,25 @@ class CartPoleRollout(Workload):
     @classmethod
     def units_per_step_total(cls, args, world):
         return cls.n_envs * cls._horizon(args) * world
+
+
+class I2PRollout(CartPoleRollout):
+    """The four inverted-double-pendulum tasks of zoo/conf/task/BI2P*.yaml through the collection loop, one launch
+    (emei_i2p_rollout_*): the step kernel's arithmetic, one env per thread."""
+
+    key = "i2p_rollout"
+    title = "BoundaryInvertedDoublePendulumSwingUp fused rollout, 2^20 envs/GPU x horizon steps per launch, freq_rate=1, in-kernel random policy + TimeLimit + auto-reset (SURVEY 8f ranks 1+3)"
+    kernel = "emei::rollout_ref_kernel<RefI2P<float>>"
+    kernel_f64 = "emei::rollout_ref_kernel<RefI2P<double>>"
+    env_id, freq_rate = "BoundaryInvertedDoublePendulumSwingUp-v0", 1
+    state_bytes = 24
+    alg_fp_ops = alg_sfu_ops = alg_fp64_ops = None
+    bound = "hbm"  # no stated operation count for the 3x3 solve: reported against the (tiny) HBM traffic + issue utilisation only
+    inst_per_unit = None
+    cpu_kind = "i2p"
+
+    def setup_e2e(self):
+        return Workload.setup_e2e(self)
 
 
 class CartPoleRolloutRecord(CartPoleRollout):
@@ -927,7 +950,7 @@ class ChargedBallRollout(Workload):
 
 WORKLOADS = {w.key: w for w in (IPStep, CartPoleStep, CartPoleStepLarge, I2PStep, HopperScoring, HalfCheetahScoring, HopperSeqScoring,
                                 HalfCheetahSeqScoring, ChargedBall, ScoringSweep, ScoringSweepSeq, CartPoleRollout, CartPoleRolloutRecord,
-                                ChargedBallRollout)}
+                                I2PRollout, ChargedBallRollout)}
 
 
 def workload_name(W, args):
@@ -1288,9 +1311,12 @@ def measure(wl, ctx, K, W, args, want_e2e=True):
     }
     mm = math_model(wl, wl.units, step_s, sm_mhz, peak)
     if wl.bound == "math" and mm is not None:  # no per-unit HBM traffic to speak of: the roofline is the algorithmic math
-        binding = "sfu" if mm["t_sfu_us"] >= mm["t_fp_us"] else "fp32"
-        ops = wl.alg_sfu_ops if binding == "sfu" else wl.alg_fp_ops
-        pk = mm["peaks"]["sfu_ops_per_s" if binding == "sfu" else "fp32_lane_ops_per_s"]
+        if wl.f64:
+            binding, ops, pk = "fp64", mm["peaks"]["fp64_ops_per_unit"], mm["peaks"]["fp64_ops_per_s"]
+        else:
+            binding = "sfu" if mm["t_sfu_us"] >= mm["t_fp_us"] else "fp32"
+            ops = wl.alg_sfu_ops if binding == "sfu" else wl.alg_fp_ops
+            pk = mm["peaks"]["sfu_ops_per_s" if binding == "sfu" else "fp32_lane_ops_per_s"]
         roofline = {
             "bound": "math", "achieved": ops * wl.units / step_s / 1e12, "peak": pk / 1e12, "unit": f"T {binding} op/s (algorithmic)",
             "frac": mm["frac_of_slower_bound"], "traffic": None, "kernel": wl.kernel_name(), "kernel_ms_per_launch": ms_per_step,

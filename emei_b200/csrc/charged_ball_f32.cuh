@@ -10,6 +10,7 @@
 // branches (on the circle: two sincos; free flight: four FMAs) use the lean float32 math of
 // f32math.cuh; only a landing (rare) evaluates asin / fmod / sqrt through libm.
 #pragma once
+#include <cstdlib>
 #include "common.cuh"
 #include "f32math.cuh"
 
@@ -169,8 +170,10 @@ __device__ __forceinline__ float cb_env_step(CBRegs& e, float E, const ChargedBa
   return fmaf(-sqrt_fast(fmaf(f.x, f.x, f.y * f.y)), k.inv_r, 1.0f);  // charged_ball.py:158-160
 }
 
-template <int AK>
-__global__ void __launch_bounds__(kBlock, 8)
+// EPT envs per thread per iteration: ALL loads of the EPT envs are issued before any math, so EPT x 26 bytes per thread are in
+// flight (the kernel is bound by memory latency x bytes in flight: ncu long-scoreboard stalls, 0.96 eligible warps per cycle).
+template <int AK, int EPT, int MINB>
+__global__ void __launch_bounds__(kBlock, MINB)
     charged_ball_step_f32_kernel(uint8_t* on_circle, float2* circle, float4* free_state, const void* __restrict__ action,
                                  float* __restrict__ reward, uint8_t* __restrict__ done, double* stats, int64_t n,
                                  const ChargedBallF32Consts k) {
@@ -179,39 +182,79 @@ __global__ void __launch_bounds__(kBlock, 8)
   pdl_trigger();
   pdl_wait();
 #pragma unroll 1
-  for (int64_t i = static_cast<int64_t>(blockIdx.x) * kBlock + threadIdx.x; i < n; i += stride) {
+  for (int64_t i0 = static_cast<int64_t>(blockIdx.x) * kBlock + threadIdx.x; i0 < n; i0 += stride * EPT) {
     // all loads first
-    const uint8_t on_u8 = on_circle[i];
-    const float2 c2 = circle[i];
-    CBRegs e;
-    e.f = free_state[i];
-    const float a = load_action_f32<AK>(action, i);
-    e.on = on_u8 != 0;
-    e.theta = c2.x;
-    e.omega = c2.y;
-    cb_prepare(e);
-    const float rew = cb_env_step(e, cb_field<AK>(a, k), k);
-    on_circle[i] = e.on ? 1 : 0;
-    circle[i] = make_float2(e.theta, e.omega);
-    free_state[i] = e.f;
-    reward[i] = rew;
-    done[i] = 0;  // charged_ball.py:110-111
-    r_acc += rew;
+    uint8_t on_u8[EPT];
+    float2 c2[EPT];
+    float a[EPT];
+    CBRegs e[EPT];
+#pragma unroll
+    for (int u = 0; u < EPT; ++u) {
+      const int64_t i = i0 + u * stride;
+      if (i < n) {
+        on_u8[u] = on_circle[i];
+        c2[u] = circle[i];
+        e[u].f = free_state[i];
+        a[u] = load_action_f32<AK>(action, i);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < EPT; ++u) {
+      const int64_t i = i0 + u * stride;
+      if (i < n) {
+        e[u].on = on_u8[u] != 0;
+        e[u].theta = c2[u].x;
+        e[u].omega = c2[u].y;
+        cb_prepare(e[u]);
+        const float rew = cb_env_step(e[u], cb_field<AK>(a[u], k), k);
+        on_circle[i] = e[u].on ? 1 : 0;
+        circle[i] = make_float2(e[u].theta, e[u].omega);
+        free_state[i] = e[u].f;
+        reward[i] = rew;
+        done[i] = 0;  // charged_ball.py:110-111
+        r_acc += rew;
+      }
+    }
   }
   block_stats_accumulate_counts(stats, static_cast<double>(r_acc), 0u);
+}
+
+// Launch shape = <envs per thread><min blocks per SM>.  Measured on the B200 (2^26 envs, profiles/r02_c4_shapes.txt): 1 env x 8 CTAs
+// (32 registers, 53 KB of loads in flight per SM) 0.687 ms = 0.835 of the copy peak; 2 x 6: 0.635; 2 x 5: 0.618; 4 x 4
+// (64 registers, 106 KB in flight): 0.611 ms = 0.94; shapes that spill (4 x 5, 8 x 3) collapse.  At 2^23 envs (the 8-way
+// strong-scaled shard of BASELINE configs[3]) the two ends measure the same (84 vs 86 us), so small batches keep the shape with
+// the most CTAs.  EMEI_CB_SHAPE overrides the choice (development knob for that A/B).
+inline int cb_shape(int64_t n) {
+  static const int forced = []() {
+    const char* e = getenv("EMEI_CB_SHAPE");
+    return e ? atoi(e) : 0;
+  }();
+  if (forced) return forced;
+  return n >= (int64_t{1} << 24) ? 44 : 18;
 }
 
 inline void charged_ball_step_f32_dispatch(uint8_t* on_circle, float* circle, float* free_state, const void* action,
                                            float* reward, uint8_t* done, double* stats, int64_t n,
                                            const emei_charged_ball_params& p, cudaStream_t s) {
   const ChargedBallF32Consts k = make_cb_f32_consts(p);
-  const int grid = persistent_grid(n, kBlock, 8);
   float2* c2 = reinterpret_cast<float2*>(circle);
   float4* f4 = reinterpret_cast<float4*>(free_state);
+  const int shape = cb_shape(n);
+#define EMEI_CB_LAUNCH(A, EPT, MINB)                                                                                               \
+  launch_pdl(charged_ball_step_f32_kernel<A, EPT, MINB>, persistent_grid((n + EPT - 1) / EPT, kBlock, MINB), kBlock, s, on_circle, c2, f4, \
+             action, reward, done, stats, n, k)
   switch (p.action_kind) {
 #define EMEI_AK(A)                                                                                                 \
   case A:                                                                                                          \
-    launch_pdl(charged_ball_step_f32_kernel<A>, grid, kBlock, s, on_circle, c2, f4, action, reward, done, stats, n, k); \
+    if (shape == 26) EMEI_CB_LAUNCH(A, 2, 6);                                                                      \
+    else if (shape == 25) EMEI_CB_LAUNCH(A, 2, 5);                                                                 \
+    else if (shape == 24) EMEI_CB_LAUNCH(A, 2, 4);                                                                 \
+    else if (shape == 44) EMEI_CB_LAUNCH(A, 4, 4);                                                                 \
+    else if (shape == 45) EMEI_CB_LAUNCH(A, 4, 5);                                                                 \
+    else if (shape == 43) EMEI_CB_LAUNCH(A, 4, 3);                                                                 \
+    else if (shape == 83) EMEI_CB_LAUNCH(A, 8, 3);                                                                 \
+    else if (shape == 82) EMEI_CB_LAUNCH(A, 8, 2);                                                                 \
+    else EMEI_CB_LAUNCH(A, 1, 8);                                                                                  \
     break;
     EMEI_AK(EMEI_ACTION_DISCRETE_U8)
     EMEI_AK(EMEI_ACTION_DISCRETE_I32)
@@ -219,6 +262,7 @@ inline void charged_ball_step_f32_dispatch(uint8_t* on_circle, float* circle, fl
     EMEI_AK(EMEI_ACTION_CONTINUOUS_F32)
     EMEI_AK(EMEI_ACTION_CONTINUOUS_F64)
 #undef EMEI_AK
+#undef EMEI_CB_LAUNCH
   }
 }
 

@@ -352,18 +352,29 @@ __global__ void __launch_bounds__(kBlock)
                              const ChargedBallConsts<R> k) {
   const int64_t stride = static_cast<int64_t>(gridDim.x) * kBlock;
   double r_acc = 0.0;
-  for (int64_t i = static_cast<int64_t>(blockIdx.x) * kBlock + threadIdx.x; i < n; i += stride) {
-    bool on = on_circle[i] != 0;
-    R theta, omega;
+  // one env ahead: the next iteration's state is requested before this iteration's math (the float64 mode moves 108 B per
+  // env and is bound by bytes in flight x memory latency, like the float32 kernel before it took four envs per thread)
+  auto load_env = [&](int64_t j, uint8_t& on_u8, R& th, R& om, Vec4<R>& ff, R& EE) {
+    on_u8 = on_circle[j];
     if constexpr (sizeof(R) == 4) {
-      const float2 c2 = reinterpret_cast<const float2*>(circle)[i];
-      theta = c2.x, omega = c2.y;
+      const float2 c2 = reinterpret_cast<const float2*>(circle)[j];
+      th = c2.x, om = c2.y;
     } else {
-      const double2 c2 = reinterpret_cast<const double2*>(circle)[i];
-      theta = c2.x, omega = c2.y;
+      const double2 c2 = reinterpret_cast<const double2*>(circle)[j];
+      th = c2.x, om = c2.y;
     }
-    Vec4<R> f = Vec4<R>::load(free_state + 4 * i);  // x, y, vx, vy
-    const R E = load_force<R>(action, i, k.action_kind, k.charge);  // charged_ball.py:155-156,169-170
+    ff = Vec4<R>::load(free_state + 4 * j);                       // x, y, vx, vy
+    EE = load_force<R>(action, j, k.action_kind, k.charge);      // charged_ball.py:155-156,169-170
+  };
+  int64_t i = static_cast<int64_t>(blockIdx.x) * kBlock + threadIdx.x;
+  uint8_t on_u8 = 0, on_n = 0;
+  R theta = R(0), omega = R(0), E = R(0), theta_n = R(0), omega_n = R(0), E_n = R(0);
+  Vec4<R> f = {R(0), R(0), R(0), R(0)}, f_n = f;
+  if (i < n) load_env(i, on_u8, theta, omega, f, E);
+  for (; i < n; i += stride) {
+    const int64_t i_next = i + stride;
+    if (i_next < n) load_env(i_next, on_n, theta_n, omega_n, f_n, E_n);
+    bool on = on_u8 != 0;
     const R rew = charged_ball_env_step<R, F32FORCE>(on, theta, omega, f, E, k);
     on_circle[i] = on ? 1 : 0;
     if constexpr (sizeof(R) == 4)
@@ -374,6 +385,7 @@ __global__ void __launch_bounds__(kBlock)
     reward[i] = rew;
     done[i] = 0;  // charged_ball.py:110-111
     r_acc += static_cast<double>(rew);
+    on_u8 = on_n, theta = theta_n, omega = omega_n, f = f_n, E = E_n;
   }
   block_stats_accumulate_counts(stats, r_acc, 0u);
 }
