@@ -132,12 +132,12 @@ __device__ __forceinline__ unsigned long long tma_now() {
 // Chunk c = envs [512 c, 512 c + 512); warp w of a group owns the 64 contiguous envs 512 c + 64 w ..: lane l takes
 // 64 w + l and 64 w + 32 + l.
 template <bool IP, int AK, int FR, bool HAS_OBS, int GROUPS = kTmaGroups, bool BULK = false>
-__global__ void __launch_bounds__(GROUPS * kBlock, GROUPS == 4 ? 1 : 2)
+__global__ void __launch_bounds__(GROUPS * kBlock, 4 / GROUPS)
     cartpole_step_f32_tma_kernel(const float4* state_in, float4* state_out, float4* obs_out,
                                  const void* __restrict__ action, float* __restrict__ reward, uint8_t* __restrict__ done,
                                  double* stats, uint32_t n, int n_slots, int flags, const CartPoleF32Consts k) {
-  // flags: bit 0 = the action array is 16-byte aligned (staged by TMA); bits 8.. = the consumer group whose first
-  // thread requests the first ring-full (kTmaProducerGroup)
+  // flags: bit 0 = the action array is 16-byte aligned (staged by TMA); bit 1 = prefetch the first ring-full into L2 before
+  // griddepcontrol.wait; bits 8.. = the consumer group whose first thread requests the first ring-full (kTmaProducerGroup)
   const int action_via_tma = flags & 1;
   const uint32_t producer_tid = static_cast<uint32_t>((flags >> 8) & 0xff) * kBlock;
   using f32::f2;
@@ -164,6 +164,23 @@ __global__ void __launch_bounds__(GROUPS * kBlock, GROUPS == 4 ? 1 : 2)
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   pdl_trigger();  // let the next step kernel of the rollout be staged behind this one
+  // L2 prefetch of this CTA's first ring-full BEFORE the grid dependency resolves.  A prefetch returns nothing to the SM and
+  // L2 is the device's point of coherence, so it is architecturally invisible: if the previous kernel is still writing these
+  // lines (the same batch stepped again) they are in L2 already and the prefetch is a hit; if they are cold (another batch,
+  // a state set from the host) the DRAM reads start while the previous grid's stragglers drain -- the 1-2 us between
+  // griddepcontrol.wait and the first chunk's landing (profiles/r02_c2_chunk_pipeline_trace.txt) shrink to an L2 hit.
+  if ((flags & 2) && tid == kBlock * (GROUPS > 1 ? 1 : 0)) {  // a thread that neither initialises barriers nor issues the loads
+    uint32_t first = my_chunks < static_cast<uint32_t>(n_slots) ? my_chunks : static_cast<uint32_t>(n_slots);
+    const uint32_t depth = static_cast<uint32_t>((flags >> 16) & 0xff);  // development knob: 0 = the whole first ring-full
+    if (depth != 0 && depth < first) first = depth;
+    for (uint32_t j = 0; j < first; ++j) {
+      const uint32_t base = (blockIdx.x + j * gridDim.x) * kChunk;
+      const uint32_t cnt = n - base < kChunk ? n - base : kChunk;
+      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(state_in + base), "r"(cnt * 16u) : "memory");
+      if (action_via_tma && cnt == kChunk)
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(act + base), "r"(kChunk * static_cast<uint32_t>(sizeof(ActT))) : "memory");
+    }
+  }
   __syncthreads();
   pdl_wait();     // the previous kernel in the stream (the step that wrote state_in) has completed
 
@@ -428,6 +445,13 @@ __global__ void __launch_bounds__(kSmallBlock)
   float rew = 0.f;
   bool notdone = true;
   pdl_trigger();
+  // L2 prefetch of this thread's inputs before the grid dependency resolves (architecturally invisible: see the TMA kernel):
+  // the loads after griddepcontrol.wait then hit L2 instead of paying the DRAM latency on the critical path of a 1.7 us launch
+  if (i < n) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(state_in + i));
+    if ((threadIdx.x & 15u) == 0)
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(static_cast<const char*>(action) + static_cast<size_t>(i) * sizeof(typename ActionStorage<AK>::type)));
+  }
   pdl_wait();
   if (i < n) {
     float4 y = state_in[i];
@@ -526,7 +550,13 @@ inline void launch_cartpole_f32_tma(int ak, cudaStream_t s, const float* state_i
     float4* out4 = reinterpret_cast<float4*>(state_out) + off;
     float4* obs4 = obs_out ? reinterpret_cast<float4*>(obs_out) + off : nullptr;
     const void* act = static_cast<const char*>(action) + off * action_bytes;
-    const int act_tma = ((reinterpret_cast<uintptr_t>(act) & 15u) == 0 ? 1 : 0) | (kTmaProducerGroup << 8);
+    // bit 1 + bits 16..: L2 prefetch of the first `depth` chunks before the grid dependency resolves.  Measured (kbench,
+    // profiles/r02_kbench_c2_prefetch.txt): at 2^20 envs no prefetch 9.42 us, depth 1: 9.01, 3: 8.46, 4: 8.54, 6: 8.72, 8: 8.89,
+    // the whole ring-full: 9.85 (the early CTAs' reads then compete with the previous grid's stragglers); at 2^22 envs
+    // depth 6-8 is best (32.2 -> 29.9 us), at 2^18 depth 3 (4.70 -> 3.77 us).
+    const int64_t per_cta = (chunks + grid - 1) / grid;
+    const int depth = static_cast<int>(per_cta / 5 + 1 < 3 ? 3 : (per_cta / 5 + 1 > 8 ? 8 : per_cta / 5 + 1));
+    const int act_tma = ((reinterpret_cast<uintptr_t>(act) & 15u) == 0 ? 1 : 0) | 2 | (kTmaProducerGroup << 8) | (depth << 16);
     switch (ak) {
 #define EMEI_AK(A)                                                                                                       \
   case A:                                                                                                                \

@@ -138,7 +138,7 @@ float time_stream(F launch, int K, cudaStream_t s, int reps = 5) {
 
 // shape variants of the shipped kernel: GROUPS consumer groups per CTA, BULK stores, CTAs per SM, ring budget
 template <int GROUPS, bool BULK>
-void run_tma2(const char* name, Ring& R, uint32_t n, int K, cudaStream_t s, int ctas_per_sm, int budget_kb, int producer_group = 0) {
+void run_tma2(const char* name, Ring& R, uint32_t n, int K, cudaStream_t s, int ctas_per_sm, int budget_kb, int producer_group = 0, int prefetch = 0, int depth = 0) {
   SKIP(name);
   emei_cartpole_params p = {};
   p.gravity = 9.8; p.mass_pole = 0.1; p.total_mass = 1.1; p.length = 0.5; p.pole_mass_length = 0.05; p.force_mag = 10.0;
@@ -158,7 +158,7 @@ void run_tma2(const char* name, Ring& R, uint32_t n, int K, cudaStream_t s, int 
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   auto launch = [&](int i) {
     int j = i % ring;
-    launch_pdl_smem(kern, grid, GROUPS * kBlock, smem, s, (const float4*)R.in[j], (float4*)R.out[j], (float4*)nullptr, (const void*)R.act[j], R.rew[j], R.done[j], stats, n, n_slots, 1 | (producer_group << 8), k);
+    launch_pdl_smem(kern, grid, GROUPS * kBlock, smem, s, (const float4*)R.in[j], (float4*)R.out[j], (float4*)nullptr, (const void*)R.act[j], R.rew[j], R.done[j], stats, n, n_slots, 1 | (prefetch ? 2 : 0) | (producer_group << 8) | (depth << 16), k);
   };
   float us = time_graph(launch, K, s);
   CK(cudaGetLastError());
@@ -263,7 +263,7 @@ void run_trace(Ring& R, uint32_t n, cudaStream_t s) {
   const int ring = (int)R.in.size();
   auto launch = [&](int i) {
     int j = i % ring;
-    launch_pdl_smem(kern, grid, kTmaThreads, smem, s, (const float4*)R.in[j], (float4*)R.out[j], (float4*)nullptr, (const void*)R.act[j], R.rew[j], R.done[j], stats, n, n_slots, 1 | (kTmaProducerGroup << 8), k);
+    launch_pdl_smem(kern, grid, kTmaThreads, smem, s, (const float4*)R.in[j], (float4*)R.out[j], (float4*)nullptr, (const void*)R.act[j], R.rew[j], R.done[j], stats, n, n_slots, 1 | 2 | (kTmaProducerGroup << 8) | (3 << 16), k);
   };
   for (int i = 0; i < 40; ++i) launch(i);  // steady state, untraced
   CK(cudaStreamSynchronize(s));
@@ -350,7 +350,29 @@ int main(int argc, char** argv) {
   run_tma2<4, false>("r2 G4 direct stores, producer = group 0", R, n, K, s, 1, 208, 0);
   run_tma2<4, false>("r2 G4 direct stores, producer = group 1", R, n, K, s, 1, 208, 1);
   run_tma2<4, false>("r2 G4 direct stores, producer = group 2", R, n, K, s, 1, 208, 2);
-  run_tma2<4, false>("r2 G4 direct stores, producer = group 3 (shipped)", R, n, K, s, 1, 208, 3);
+  run_tma2<4, false>("r2 G4 direct stores, producer = group 3", R, n, K, s, 1, 208, 3);
+  run_tma2<4, false>("r2 G4 producer 3 + L2 prefetch before the grid dependency (shipped)", R, n, K, s, 1, 208, 3, 1);
+  run_tma2<2, false>("r2 G2 half-SM 10 slots + L2 prefetch", R, n, K, s, 1, 104, 1, 1);
+  run_tma2<2, false>("r2 G2 2 CTAs/SM 7 slots + L2 prefetch", R, n, K, s, 2, 104, 1, 1);
+  run_tma2<2, false>("r3 G2 2 CTAs/SM 8 slots + L2 prefetch, producer g0", R, n, K, s, 2, 104, 0, 1);
+  run_tma2<2, false>("r3 G2 2 CTAs/SM + L2 prefetch depth 2", R, n, K, s, 2, 104, 1, 1, 2);
+  run_tma2<2, false>("r3 G2 2 CTAs/SM + L2 prefetch depth 4", R, n, K, s, 2, 104, 1, 1, 4);
+  run_tma2<1, false>("r3 G1 4 CTAs/SM 4 slots + L2 prefetch", R, n, K, s, 4, 48, 0, 1);
+  run_tma2<1, false>("r3 G1 4 CTAs/SM 4 slots, no prefetch", R, n, K, s, 4, 48, 0, 0);
+  run_tma2<1, false>("r3 G1 3 CTAs/SM 5 slots + L2 prefetch", R, n, K, s, 3, 64, 0, 1);
+  run_tma2<4, false>("r4 G4 + L2 prefetch depth 1", R, n, K, s, 1, 208, 3, 1, 1);
+  run_tma2<4, false>("r4 G4 + L2 prefetch depth 3", R, n, K, s, 1, 208, 3, 1, 3);
+  run_tma2<4, false>("r4 G4 + L2 prefetch depth 4", R, n, K, s, 1, 208, 3, 1, 4);
+  run_tma2<4, false>("r4 G4 + L2 prefetch depth 5", R, n, K, s, 1, 208, 3, 1, 5);
+  run_tma2<4, false>("r4 G4 + L2 prefetch depth 6", R, n, K, s, 1, 208, 3, 1, 6);
+  run_tma2<4, false>("r4 G4 + L2 prefetch depth 8", R, n, K, s, 1, 208, 3, 1, 8);
+  run_tma2<4, false>("r4 G4 no prefetch", R, n, K, s, 1, 208, 3, 0, 0);
+  run_tma2<2, false>("r4 G2 2 CTAs/SM + L2 prefetch depth 1", R, n, K, s, 2, 104, 1, 1, 1);
+  run_tma2<2, false>("r4 G2 2 CTAs/SM + L2 prefetch depth 2", R, n, K, s, 2, 104, 1, 1, 2);
+  run_tma2<2, false>("r4 G2 2 CTAs/SM + L2 prefetch depth 3", R, n, K, s, 2, 104, 1, 1, 3);
+  run_tma2<2, false>("r4 G2 2 CTAs/SM no prefetch", R, n, K, s, 2, 104, 1, 0, 0);
+  run_tma2<4, false>("r3 G4 + L2 prefetch depth 2", R, n, K, s, 1, 208, 3, 1, 2);
+  run_tma2<4, false>("r3 G4 + L2 prefetch depth 4", R, n, K, s, 1, 208, 3, 1, 4);
   run_tma2<4, true>("r2 G4 BULK stores", R, n, K, s, 1, 216);
   run_tma2<2, false>("r2 G2 half-SM, 1 CTA/SM/kernel, 10 slots", R, n, K, s, 1, 104);
   run_tma2<2, false>("r2 G2 half-SM, 1 CTA/SM/kernel, 8 slots", R, n, K, s, 1, 84);
