@@ -357,6 +357,16 @@ class CartPoleStep(Workload):
         j = i % len(self.envs)
         self.envs[j].step(self.acts[j])
 
+    def restore_inputs(self):
+        """Put the synthetic states of SURVEY 8(d) back into the buffers the first timed step of every env reads (outside the
+        timed region).  The step kernels never reset, and the warm-up replays advance every env by hundreds of steps under
+        constant actions: poles spin up beyond the integrator's guard (|theta_dot| > 39 rad/s) and the timed steps would
+        measure the cold redo path instead of the workload's state distribution."""
+        if getattr(self, "_restore", None) is None:  # first call (before capture): remember the buffers and their contents
+            self._restore = [(e._engine._bufs[e._engine._cur], e._engine._bufs[e._engine._cur].clone()) for e in self.envs]
+        for buf, init in self._restore:
+            buf.copy_(init)
+
     def setup_e2e(self):
         import torch
 
@@ -1161,6 +1171,10 @@ def measure(wl, ctx, K, W, args, want_e2e=True):
     if not wl.use_graph:
         launch_mode = "stream"
     launches0 = _lib.launch_count
+    restore = getattr(wl, "restore_inputs", None)
+    if restore is not None:
+        restore()
+        torch.cuda.synchronize()
     graph = None
     ev_in = None
     if launch_mode == "graph":  # launch-bound steps: K launches captured once, replayed as one graph
@@ -1203,6 +1217,14 @@ def measure(wl, ctx, K, W, args, want_e2e=True):
         if stop:
             break
     _lib.call("emei_stats_reset", wl.stats.data_ptr(), torch.cuda.current_stream(dev).cuda_stream, launches=0)
+    if restore is not None and graph is not None:  # the graph reads the buffers remembered before its capture
+        restore()
+    if wl.use_graph:
+        # a 20-step region touches only the first batches of the ring (C1: 20 of 1024), which the warm-up replays left in
+        # L2: write 256 MB (> the 126 MB L2) so that every timed step reads its inputs from HBM
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+        flush.zero_()
+        del flush
     launches0 = _lib.launch_count
     if world > 1:
         dist.barrier()
@@ -1344,6 +1366,10 @@ def measure(wl, ctx, K, W, args, want_e2e=True):
         hb = getattr(args, "host_binding", None)
         protocol["host_binding"] = (f"rank 0 bound to {len(hb)} CPUs local to its GPU's NUMA node" if hb else
                                     "none: the host exposes one NUMA node / no per-GPU CPU locality")
+    if restore is not None and launch_mode == "graph":
+        protocol["inputs"] = ("the synthetic states of SURVEY 8(d) are copied back into every env's input buffer after the warm-up replays, outside "
+                              "the timed region (the step kernels never reset: warm-up alone would spin the poles beyond the integrator's guard); "
+                              "then 256 MB are written to flush the 126 MB L2, so every timed step reads from HBM")
     if launch_mode == "graph":
         protocol["ms_per_step_including_graph_launch"] = ms_outer / K
         protocol["note"] = ("events recorded around graph.replay() also contain the graph's launch, a one-off per replay: "

@@ -24,7 +24,7 @@ constexpr int kTmaGroups = 4;                                 // consumer groups
 constexpr int kTmaThreads = kTmaGroups * kBlock;              // 1024 threads: 8 warps per scheduler at <= 64 registers; thread 0 doubles as the TMA producer
 constexpr uint32_t kChunk = 2 * kBlock;                       // envs per chunk
 constexpr int kTmaSmemBudget = 208 * 1024;                    // ring bytes (of 227 KB per SM)
-constexpr int kTmaMaxSlots = 24;
+constexpr int kTmaMaxSlots = 32;
 constexpr uint32_t kChunkOutBytes = kChunk * 5;               // BULK: staged reward (4 B) + done (1 B) of a chunk
 // The first ring-full (up to 16 chunks x 2 bulk copies, ~1 000 instructions of one thread) is requested by the first
 // thread of the LAST consumer group: with 13.8 chunks per SM the groups own 4, 4, 3, 3 (or 4, 3, 3, 3) chunks, so the
@@ -131,11 +131,15 @@ __device__ __forceinline__ unsigned long long tma_now() {
 // them with three bulk copies shared -> global; only for launches that never recycle a slot (the host decides).
 // Chunk c = envs [512 c, 512 c + 512); warp w of a group owns the 64 contiguous envs 512 c + 64 w ..: lane l takes
 // 64 w + l and 64 w + 32 + l.
-template <bool IP, int AK, int FR, bool HAS_OBS, int GROUPS = kTmaGroups, bool BULK = false>
-__global__ void __launch_bounds__(GROUPS * kBlock, 4 / GROUPS)
+template <bool IP, int AK, int FR, bool HAS_OBS, int GROUPS = kTmaGroups, bool BULK = false, int GSZ = kBlock>
+__global__ void __launch_bounds__(GROUPS * GSZ, 1024 / (GROUPS * GSZ))
     cartpole_step_f32_tma_kernel(const float4* state_in, float4* state_out, float4* obs_out,
                                  const void* __restrict__ action, float* __restrict__ reward, uint8_t* __restrict__ done,
                                  double* stats, uint32_t n, int n_slots, int flags, const CartPoleF32Consts k) {
+  // GSZ threads per consumer group, 2 * GSZ envs per chunk (the names below shadow the namespace-level defaults)
+  constexpr int kBlock = GSZ;
+  constexpr uint32_t kChunk = 2 * GSZ;
+  [[maybe_unused]] constexpr uint32_t kChunkOutBytes = kChunk * 5;
   // flags: bit 0 = the action array is 16-byte aligned (staged by TMA); bit 1 = prefetch the first ring-full into L2 before
   // griddepcontrol.wait; bits 8.. = the consumer group whose first thread requests the first ring-full (kTmaProducerGroup)
   const int action_via_tma = flags & 1;
@@ -469,8 +473,8 @@ __global__ void __launch_bounds__(kSmallBlock)
 
 // slots, dynamic shared memory bytes for an action element size
 inline void tma_ring_shape(int action_bytes, int64_t chunks_per_cta, int* n_slots, size_t* smem_bytes, int groups = kTmaGroups,
-                           bool bulk = false, int budget = kTmaSmemBudget) {
-  const int slot_bytes = static_cast<int>(kChunk) * (16 + action_bytes) + (bulk ? static_cast<int>(kChunkOutBytes) : 0);
+                           bool bulk = false, int budget = kTmaSmemBudget, int gsz = kBlock) {
+  const int slot_bytes = 2 * gsz * (16 + action_bytes) + (bulk ? 2 * gsz * 5 : 0);
   int s = budget / slot_bytes;
   if (s > kTmaMaxSlots) s = kTmaMaxSlots;
   if (s > chunks_per_cta) s = static_cast<int>(chunks_per_cta);
@@ -478,7 +482,7 @@ inline void tma_ring_shape(int action_bytes, int64_t chunks_per_cta, int* n_slot
   while (s * slot_bytes > budget) s -= groups;
   if (s < groups) s = groups;
   *n_slots = s;
-  *smem_bytes = static_cast<size_t>(s) * slot_bytes + 2 * s * sizeof(uint64_t) + (groups * kBlock / 32) * (sizeof(double) + sizeof(unsigned)) + 16;
+  *smem_bytes = static_cast<size_t>(s) * slot_bytes + 2 * s * sizeof(uint64_t) + (groups * gsz / 32) * (sizeof(double) + sizeof(unsigned)) + 16;
 }
 
 // opt in to > 48 KB of dynamic shared memory: the attribute is PER DEVICE, so it is set once per (kernel

@@ -137,7 +137,7 @@ float time_stream(F launch, int K, cudaStream_t s, int reps = 5) {
 }
 
 // shape variants of the shipped kernel: GROUPS consumer groups per CTA, BULK stores, CTAs per SM, ring budget
-template <int GROUPS, bool BULK>
+template <int GROUPS, bool BULK, int GSZ = kBlock>
 void run_tma2(const char* name, Ring& R, uint32_t n, int K, cudaStream_t s, int ctas_per_sm, int budget_kb, int producer_group = 0, int prefetch = 0, int depth = 0) {
   SKIP(name);
   emei_cartpole_params p = {};
@@ -145,20 +145,20 @@ void run_tma2(const char* name, Ring& R, uint32_t n, int K, cudaStream_t s, int 
   p.x_threshold = 5.0; p.theta_threshold = 0.2; p.dt = 0.02; p.freq_rate = 4; p.variant = EMEI_CARTPOLE_SWINGUP;
   p.action_kind = EMEI_ACTION_CONTINUOUS_F32;
   CartPoleF32Consts k = make_cartpole_f32_consts(p);
-  const int64_t chunks = (n + kChunk - 1) / kChunk;
+  const int64_t chunks = (n + 2 * GSZ - 1) / (2 * GSZ);
   const int64_t cap = (int64_t)kNumSMs * ctas_per_sm;
   const int grid = (int)(chunks < cap ? chunks : cap);
   int n_slots; size_t smem;
-  tma_ring_shape(4, (chunks + grid - 1) / grid, &n_slots, &smem, GROUPS, BULK, budget_kb * 1024);
+  tma_ring_shape(4, (chunks + grid - 1) / grid, &n_slots, &smem, GROUPS, BULK, budget_kb * 1024, GSZ);
   const bool recycles = (chunks + grid - 1) / grid > n_slots;
   if (BULK && recycles) { printf("%-52s skipped: BULK needs a ring that holds the CTA's whole share\n", name); return; }
   double* stats; CK(cudaMalloc(&stats, 16)); CK(cudaMemset(stats, 0, 16));
   const int ring = (int)R.in.size();
-  auto kern = cartpole_step_f32_tma_kernel<false, EMEI_ACTION_CONTINUOUS_F32, 4, false, GROUPS, BULK>;
+  auto kern = cartpole_step_f32_tma_kernel<false, EMEI_ACTION_CONTINUOUS_F32, 4, false, GROUPS, BULK, GSZ>;
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   auto launch = [&](int i) {
     int j = i % ring;
-    launch_pdl_smem(kern, grid, GROUPS * kBlock, smem, s, (const float4*)R.in[j], (float4*)R.out[j], (float4*)nullptr, (const void*)R.act[j], R.rew[j], R.done[j], stats, n, n_slots, 1 | (prefetch ? 2 : 0) | (producer_group << 8) | (depth << 16), k);
+    launch_pdl_smem(kern, grid, GROUPS * GSZ, smem, s, (const float4*)R.in[j], (float4*)R.out[j], (float4*)nullptr, (const void*)R.act[j], R.rew[j], R.done[j], stats, n, n_slots, 1 | (prefetch ? 2 : 0) | (producer_group << 8) | (depth << 16), k);
   };
   float us = time_graph(launch, K, s);
   CK(cudaGetLastError());
@@ -166,9 +166,9 @@ void run_tma2(const char* name, Ring& R, uint32_t n, int K, cudaStream_t s, int 
   float us20g = time_graph(launch, 20, s, reps20);
   float us20s = time_stream(launch, 20, s, reps20);
   CK(cudaGetLastError());
-  int occ = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, GROUPS * kBlock, smem);
+  int occ = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, GROUPS * GSZ, smem);
   printf("%-52s grid=%4d thr=%4d slots=%2d smem=%6zu occ=%d  graph K=%d: %6.2f us  %5.0f GB/s | K=20 graph %6.2f us, K=20 stream launches %6.2f us\n",
-         name, grid, GROUPS * kBlock, n_slots, smem, occ, K, us, 41.0 * n / us * 1e-3, us20g, us20s);
+         name, grid, GROUPS * GSZ, n_slots, smem, occ, K, us, 41.0 * n / us * 1e-3, us20g, us20s);
   cudaFree(stats);
 }
 
@@ -360,6 +360,11 @@ int main(int argc, char** argv) {
   run_tma2<1, false>("r3 G1 4 CTAs/SM 4 slots + L2 prefetch", R, n, K, s, 4, 48, 0, 1);
   run_tma2<1, false>("r3 G1 4 CTAs/SM 4 slots, no prefetch", R, n, K, s, 4, 48, 0, 0);
   run_tma2<1, false>("r3 G1 3 CTAs/SM 5 slots + L2 prefetch", R, n, K, s, 3, 64, 0, 1);
+  run_tma2<8, false, 128>("r5 G8 x 128 threads, 256-env chunks, prefetch depth 6", R, n, K, s, 1, 208, 7, 1, 6);
+  run_tma2<8, false, 128>("r5 G8 x 128 threads, 256-env chunks, prefetch depth 8", R, n, K, s, 1, 208, 7, 1, 8);
+  run_tma2<8, false, 128>("r5 G8 x 128 threads, 256-env chunks, prefetch depth 4", R, n, K, s, 1, 208, 7, 1, 4);
+  run_tma2<8, false, 128>("r5 G8 x 128 threads, 256-env chunks, no prefetch", R, n, K, s, 1, 208, 7, 0, 0);
+  run_tma2<4, false>("r5 G4 + L2 prefetch depth 3 (shipped)", R, n, K, s, 1, 208, 3, 1, 3);
   run_tma2<4, false>("r4 G4 + L2 prefetch depth 1", R, n, K, s, 1, 208, 3, 1, 1);
   run_tma2<4, false>("r4 G4 + L2 prefetch depth 3", R, n, K, s, 1, 208, 3, 1, 3);
   run_tma2<4, false>("r4 G4 + L2 prefetch depth 4", R, n, K, s, 1, 208, 3, 1, 4);
