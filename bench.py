@@ -328,7 +328,7 @@ class CartPoleStep(Workload):
     alg_fp64_ops = 4 * (22 + 4 * 10 + 2 * 20) + 20 + 4  # float64: 22 plain ops + 4 divides + sin + cos per sub-step; reward cos
     cpu_kind = "c2"
     supports_f64 = True
-    inst_per_unit = 179.1  # 32 x smsp__inst_executed / envs, packed f32x2 (ncu, profiles/r01_launches_bench_c2.csv)
+    inst_per_unit = 165.8  # 32 x smsp__inst_executed / envs, packed f32x2 (ncu, profiles/r02_ncu_full_c2.txt: 5 432 964 warp instructions per 2^20-env launch)
 
     def synth(self, seed):
         return synth_cartpole(self.n_envs, seed)
@@ -396,7 +396,8 @@ class CartPoleStep(Workload):
         mb = ring * cls.n_envs * bpu / 1e6
         return {
             "envs_per_gpu": cls.n_envs, "freq_rate": cls.freq_rate, "real_time_scale": DT,
-            "l2_policy": f"inputs larger than L2: ring of {ring} independent {cls.n_envs}-env batches ({mb:.0f} MB of step traffic) rotated every launch",
+            "l2_policy": f"inputs larger than L2: ring of {ring} independent {cls.n_envs}-env batches ({mb:.0f} MB of step traffic) rotated every launch; "
+                         "L2 flushed (256 MB written) before the timed region",
         }
 
     @classmethod
