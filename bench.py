@@ -806,7 +806,7 @@ class CartPoleRollout(Workload):
     supports_f64 = True
     state_bytes = 16
     alg_fp_ops, alg_sfu_ops, alg_fp64_ops = CartPoleStep.alg_fp_ops, CartPoleStep.alg_sfu_ops, CartPoleStep.alg_fp64_ops
-    inst_per_unit = 247.1  # thread-level SASS instructions per env-step incl. divergent in-kernel resets (ncu, profiles/r01_launches_rollout*.csv)
+    inst_per_unit = 185.8  # thread-level SASS instructions per env-step incl. in-kernel resets (ncu, profiles/r02_launches_rollout.csv; 247.1 before the spare reset samples)
     cpu_kind = "c2"
     e2e_max_steps = 5
 
@@ -901,7 +901,7 @@ class ChargedBallRollout(Workload):
     scaling, use_graph, bound = "strong", False, "math"
     total = 1 << 26
     alg_fp_ops, alg_sfu_ops = ChargedBall.alg_fp_ops, ChargedBall.alg_sfu_ops
-    inst_per_unit = 166.0  # warp-level SASS instructions per env-step, all three divergent paths issued (ncu, profiles/r01_launches_c4_rollout.csv)
+    inst_per_unit = 151.3  # warp-level SASS instructions per env-step, all three divergent paths issued (ncu, profiles/r02_launches_c4_rollout.csv: second launch; 166.0 in round 1)
     cpu_kind, cpu_sample = "c4", 1 << 20
     e2e_max_steps = 5
 

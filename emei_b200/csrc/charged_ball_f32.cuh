@@ -118,11 +118,16 @@ __device__ __forceinline__ float cb_field(float a, const ChargedBallF32Consts& k
 // In a rollout nearly every warp holds balls on the ring, balls in flight AND a ball that lands in this very
 // step (5 % of env-steps, 85 % of warp-steps), so a warp issues all three paths: they are kept short and share
 // ONE sincos site (after the branches) instead of one per path.
+// FR > 0: the sub-step count is a compile-time constant (the rollout kernel's freq_rate = 1 instance has no loop at all);
+// FR = 0: k.freq_rate at run time.  Same bits either way.
+template <int FR = 0>
 __device__ __forceinline__ float cb_env_step(CBRegs& e, float E, const ChargedBallF32Consts& k) {
   bool on = e.on;
   float theta = e.theta, omega = e.omega, s = e.s, c = e.c;
   float4 f = e.f;
-  for (int sub = 0; sub < k.freq_rate; ++sub) {
+  const int n_sub = FR > 0 ? FR : k.freq_rate;
+#pragma unroll
+  for (int sub = 0; sub < n_sub; ++sub) {
     bool on_ring = on;  // took the ring path: (x, y, vx, vy) follow from the new (theta, omega)
     if (on) {
       // _get_update_info :72-78 + update_state :56-61

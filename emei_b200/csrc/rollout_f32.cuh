@@ -116,6 +116,7 @@ struct CartPoleDyn {
   // f32::cartpole_integrate<f2>), which halves the issue slots of the integration; policy, TimeLimit bookkeeping and
   // resets stay per env.
   static constexpr int kEnvsPerThread = 2;
+  static constexpr bool kSpareReset = true;  // resets are frequent and per env: keep the next sample ready (kernel comment)
   static constexpr int kMinBlocks = 3;  // 80 registers, no spills; 4 CTAs/SM (64 registers, 128 B of spills) measured the same 101 G env-steps/s
   struct Buffers {
     float4* state;
@@ -186,21 +187,27 @@ struct CartPoleDyn {
   __device__ __forceinline__ static void reset(Regs& e, const RolloutConsts& r, const Consts&, unsigned long long env, unsigned long long seed) {
     e.y = rollout_init_state(r, env, seed);
   }
+  __device__ __forceinline__ static float4 pack(const Regs& e) { return e.y; }
+  __device__ __forceinline__ static void unpack(Regs& e, const float4& v) { e.y = v; }
 };
 
-template <int AK>
+struct ChargedBallBuffers {
+  uint8_t* on_circle;
+  float2* circle;
+  float4* free_state;
+};
+
+// FR: compile-time sub-step count (0 = k.freq_rate at run time)
+template <int AK, int FR>
 struct ChargedBallDyn {
   using Consts = ChargedBallF32Consts;
   using ActT = typename ActionStorage<AK>::type;
   static constexpr bool kDiscrete = AK <= EMEI_ACTION_DISCRETE_I64;
   static constexpr int kMinBlocks = 4;
-  struct Buffers {
-    uint8_t* on_circle;
-    float2* circle;
-    float4* free_state;
-  };
+  using Buffers = ChargedBallBuffers;
   using Regs = CBRegs;
   static constexpr int kEnvsPerThread = 1;
+  static constexpr bool kSpareReset = false;  // the charged ball never terminates: every env resets at the same TimeLimit step
   __device__ __forceinline__ static void blank(Regs&) {}
   __device__ __forceinline__ static void load(Regs& e, const Buffers& b, uint32_t i) {
     e.on = b.on_circle[i] != 0;
@@ -218,13 +225,15 @@ struct ChargedBallDyn {
   __device__ __forceinline__ static float4 observation(const Regs& e) { return e.f; }  // charged_ball.py:96-97
   __device__ __forceinline__ static void step(Regs (&e)[1], const float (&a)[1], const Consts& k, float (&rew)[1],
                                               bool (&terminated)[1], float4 (&next_obs)[1]) {
-    rew[0] = cb_env_step(e[0], cb_field<AK>(a[0], k), k);
+    rew[0] = cb_env_step<FR>(e[0], cb_field<AK>(a[0], k), k);
     terminated[0] = false;  // charged_ball.py:110-111
     next_obs[0] = e[0].f;
   }
   __device__ __forceinline__ static void reset(Regs& e, const RolloutConsts&, const Consts& k, unsigned long long env, unsigned long long seed) {
     e = rollout_init_charged_ball(k.r, env, seed);
   }
+  __device__ __forceinline__ static float4 pack(const Regs& e) { return e.f; }  // unused (kSpareReset = false)
+  __device__ __forceinline__ static void unpack(Regs&, const float4&) {}
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -259,6 +268,18 @@ __global__ void __launch_bounds__(kBlock, Dyn::kMinBlocks)
   // reward sums in double: a thread's partial sums must not depend on how a horizon is split into launches
   double r_sum = 0.0, fin_ret = 0.0;
   unsigned n_term = 0, n_trunc = 0, n_fin = 0, fin_len = 0;
+  // Spare reset samples (families whose episodes end at different steps in different envs).  A reset is a divergent
+  // call of ~110 warp instructions (one Philox block + conversions; the Gaussian family: two blocks, log, sqrt,
+  // sincospi in double), and under a random policy 36 % of the 32-env warp-steps hold at least one env that needs it,
+  // so every env-step paid ~45 instructions for an event that 1.4 % of them take.  The sample of an env's NEXT
+  // episode depends only on (seed, env, episode index + 1), so it is drawn ahead of time, all lanes of a warp that
+  // lack one in the same pass every kSpareWindow steps, and parked in shared memory; a reset is then one 128-bit
+  // load, and only an env that ends two episodes inside one window takes the divergent call.  Same samples, same bits.
+  constexpr bool SPARE = Dyn::kSpareReset;
+  constexpr int kSpareWindow = 16;
+  __shared__ float4 s_spare[SPARE ? E : 1][SPARE ? kBlock : 1];
+  const bool use_spare = SPARE && r.auto_reset && r.horizon >= kSpareWindow;
+  const int max_steps = r.max_episode_steps > 0 ? r.max_episode_steps : 0x7fffffff;  // gym TimeLimit; 0 = none
   pdl_trigger();
   pdl_wait();
   if (i0 < n) {
@@ -267,9 +288,12 @@ __global__ void __launch_bounds__(kBlock, Dyn::kMinBlocks)
     bool live[E];
     int ep_step[E], ep_idx[E];
     float ep_ret[E], a_next[E];
-    uint32_t w[E][4];
+    uint32_t w[E][4], cur[E];
+    bool have_spare[E];
 #pragma unroll
     for (int e = 0; e < E; ++e) {
+      cur[e] = 0u;
+      have_spare[e] = false;
       idx[e] = i0 + static_cast<uint32_t>(e) * kBlock;
       live[e] = idx[e] < n;
       ep_step[e] = ep_idx[e] = 0;
@@ -285,23 +309,47 @@ __global__ void __launch_bounds__(kBlock, Dyn::kMinBlocks)
         Dyn::blank(ev[e]);  // a dead lane of the pair computes on zeros; nothing of it is stored or counted
       }
     }
+    const uint32_t t0_lo = static_cast<uint32_t>(r.t0);  // positions inside a Philox block need the low bits only
     for (int t = 0; t < r.horizon; ++t) {
       float a[E];
+      const uint32_t tl = t0_lo + static_cast<uint32_t>(t);  // low word of the global step r.t0 + t (uniform)
+      if constexpr (SPARE) {
+        if (use_spare && (t & (kSpareWindow - 1)) == 0) {  // uniform
+#pragma unroll
+          for (int e = 0; e < E; ++e) {
+            if (live[e] && !have_spare[e]) {
+              typename Dyn::Regs nxt = ev[e];
+              Dyn::reset(nxt, r, k, r.env_offset + idx[e],
+                         r.seed_reset + static_cast<unsigned long long>(ep_idx[e] + 1) * 0xD1B54A32D192ED03ull);
+              s_spare[e][threadIdx.x] = Dyn::pack(nxt);
+              have_spare[e] = true;
+            }
+          }
+        }
+      }
 #pragma unroll
       for (int e = 0; e < E; ++e) {
         // ---- policy
         if (r.random_policy) {  // env.action_space.sample() (zoo/util.py:57): Discrete(2) bit / Box uniform
           // counter-based stream per (seed_action, env): Discrete(2) consumes ONE bit per step (a 128-bit Philox
-          // block lasts 128 steps), Box one 32-bit word per step (top 24 bits -> [low, high))
-          const unsigned long long env = r.env_offset + idx[e];
-          const unsigned long long tg = r.t0 + static_cast<unsigned long long>(t);
+          // block lasts 128 steps: block tg >> 7, word (tg >> 5) & 3, bit tg & 31), Box one 32-bit word per step
+          // (block tg >> 2, word tg & 3, top 24 bits -> [low, high)).  The refresh tests depend on the step number
+          // only, so they are uniform branches; between refreshes a Discrete step costs a mask and a shift of the
+          // current word.
           if constexpr (Dyn::kDiscrete) {
-            if (t == 0 || (tg & 127ull) == 0) Philox::generate(r.seed_action, env, static_cast<uint32_t>(tg >> 7), kPurposeRolloutAction, w[e]);
-            const uint32_t word = select_word(w[e], static_cast<unsigned>(tg >> 5) & 3u);
-            a[e] = static_cast<float>((word >> (static_cast<unsigned>(tg) & 31u)) & 1u);
+            if (t == 0 || (tl & 31u) == 0) {
+              if (t == 0 || (tl & 127u) == 0)
+                Philox::generate(r.seed_action, r.env_offset + idx[e],
+                                 static_cast<uint32_t>((r.t0 + static_cast<unsigned long long>(t)) >> 7), kPurposeRolloutAction, w[e]);
+              cur[e] = select_word(w[e], (tl >> 5) & 3u) >> (tl & 31u);
+            }
+            a[e] = static_cast<float>(cur[e] & 1u);
+            cur[e] >>= 1;
           } else {
-            if (t == 0 || (tg & 3ull) == 0) Philox::generate(r.seed_action, env, static_cast<uint32_t>(tg >> 2), kPurposeRolloutAction, w[e]);
-            const uint32_t word = select_word(w[e], static_cast<unsigned>(tg) & 3u);
+            if (t == 0 || (tl & 3u) == 0)
+              Philox::generate(r.seed_action, r.env_offset + idx[e],
+                               static_cast<uint32_t>((r.t0 + static_cast<unsigned long long>(t)) >> 2), kPurposeRolloutAction, w[e]);
+            const uint32_t word = select_word(w[e], tl & 3u);
             a[e] = fmaf(r.act_high - r.act_low, static_cast<float>(word >> 8) * (1.0f / 16777216.0f), r.act_low);
           }
         } else {
@@ -327,7 +375,7 @@ __global__ void __launch_bounds__(kBlock, Dyn::kMinBlocks)
         // ---- TimeLimit + bookkeeping (zoo/util.py:58-73; gym TimeLimit: truncated = elapsed >= max)
         ep_step[e] += 1;
         ep_ret[e] += rew[e];
-        const bool truncated = r.max_episode_steps > 0 && ep_step[e] >= r.max_episode_steps;
+        const bool truncated = ep_step[e] >= max_steps;
         const bool done = terminated[e] || truncated;
         if constexpr (RECORD) {
           const size_t rec = static_cast<size_t>(t) * n + idx[e];
@@ -337,16 +385,23 @@ __global__ void __launch_bounds__(kBlock, Dyn::kMinBlocks)
           io.rec_timeout[rec] = truncated ? 1 : 0;
         }
         r_sum += static_cast<double>(rew[e]);
-        n_term += terminated[e] ? 1u : 0u;
-        n_trunc += truncated ? 1u : 0u;
-        if (done && r.auto_reset) {
-          n_fin += 1u;
-          fin_ret += static_cast<double>(ep_ret[e]);
-          fin_len += static_cast<unsigned>(ep_step[e]);
-          ep_idx[e] += 1;
-          Dyn::reset(ev[e], r, k, r.env_offset + idx[e], r.seed_reset + static_cast<unsigned long long>(ep_idx[e]) * 0xD1B54A32D192ED03ull);
-          ep_step[e] = 0;
-          ep_ret[e] = 0.f;
+        if (done) {
+          n_term += terminated[e] ? 1u : 0u;
+          n_trunc += truncated ? 1u : 0u;
+          if (r.auto_reset) {
+            n_fin += 1u;
+            fin_ret += static_cast<double>(ep_ret[e]);
+            fin_len += static_cast<unsigned>(ep_step[e]);
+            ep_idx[e] += 1;
+            if (SPARE && have_spare[e]) {  // the sample drawn ahead of time for exactly this episode index
+              Dyn::unpack(ev[e], s_spare[e][threadIdx.x]);
+              have_spare[e] = false;
+            } else {
+              Dyn::reset(ev[e], r, k, r.env_offset + idx[e], r.seed_reset + static_cast<unsigned long long>(ep_idx[e]) * 0xD1B54A32D192ED03ull);
+            }
+            ep_step[e] = 0;
+            ep_ret[e] = 0.f;
+          }
         }
       }
     }
@@ -405,8 +460,9 @@ inline void launch_charged_ball_rollout(int ak, uint8_t* on_circle, float* circl
   switch (ak) {
 #define EMEI_AK(A)                                                                                                       \
   case A: {                                                                                                              \
-    typename ChargedBallDyn<A>::Buffers b = {on_circle, reinterpret_cast<float2*>(circle), reinterpret_cast<float4*>(free_state)}; \
-    launch_rollout<ChargedBallDyn<A>>(b, io, n, k, r, s);                                                                \
+    ChargedBallBuffers b = {on_circle, reinterpret_cast<float2*>(circle), reinterpret_cast<float4*>(free_state)}; \
+    if (k.freq_rate == 1) launch_rollout<ChargedBallDyn<A, 1>>(b, io, n, k, r, s); /* BASELINE configs[3]: no sub-step loop */ \
+    else launch_rollout<ChargedBallDyn<A, 0>>(b, io, n, k, r, s);                                                         \
   } break;
     EMEI_AK(EMEI_ACTION_DISCRETE_U8)
     EMEI_AK(EMEI_ACTION_DISCRETE_I32)
