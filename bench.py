@@ -901,7 +901,7 @@ class ChargedBallRollout(Workload):
     scaling, use_graph, bound = "strong", False, "math"
     total = 1 << 26
     alg_fp_ops, alg_sfu_ops = ChargedBall.alg_fp_ops, ChargedBall.alg_sfu_ops
-    inst_per_unit = 151.3  # warp-level SASS instructions per env-step, all three divergent paths issued (ncu, profiles/r02_launches_c4_rollout.csv: second launch; 166.0 in round 1)
+    inst_per_unit = 139.7  # warp-level SASS instructions per env-step, all three divergent paths issued (ncu, profiles/r02_launches_c4_rollout.csv: mean of two consecutive 200-step launches, 128.1 from the reset state and 151.3 after it; 166.0 in round 1)
     cpu_kind, cpu_sample = "c4", 1 << 20
     e2e_max_steps = 5
 
