@@ -1328,7 +1328,8 @@ def measure(wl, ctx, K, W, args, want_e2e=True):
     achieved = bpu * wl.units / step_s / 1e9
     roofline = {
         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-        "peak_source": peak_src, "algorithmic_bytes_per_unit": bpu, "kernel": wl.kernel_name(),
+        "peak_source": peak_src, "frac_of_datasheet_8tbs": achieved / 8000.0,  # also against the 8 TB/s datasheet figure
+        "algorithmic_bytes_per_unit": bpu, "kernel": wl.kernel_name(),
         "kernel_ms_per_launch": ms_per_step,
         "note": "duration = CUDA-event time of ONE WHOLE STEP (timed region / steps: every kernel of the step and the gaps between launches included)",
     }
