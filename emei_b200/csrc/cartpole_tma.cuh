@@ -91,9 +91,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 // 1-D bulk copy global -> shared (TMA engine); completes `bytes` on the mbarrier.  16-byte aligned, size % 16 == 0.
 __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+#ifdef EMEI_TMA_STREAM_HINTS  // development A/B (tools/kbench): L2 evict-first policy on the streamed inputs
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(smem_u32(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
+               : "memory");
+#else
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
                "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
+#endif
 }
 
 // 1-D bulk copy shared -> global (TMA engine), bulk-group completion.  16-byte aligned, size % 16 == 0.
@@ -349,6 +357,23 @@ __global__ void __launch_bounds__(GROUPS * GSZ, 1024 / (GROUPS * GSZ))
         float4* so = state_out + i;
         float* ro = reward + i;
         uint8_t* dn = done + i;
+#if defined(EMEI_TMA_STREAM_HINTS) && EMEI_TMA_STREAM_HINTS >= 2  // development A/B: streaming (evict-first) stores
+        if (live_a) {
+          __stcs(so, na);
+          __stcs(ro, rew_a);
+          __stcs(dn, static_cast<uint8_t>(nd_a ? 0 : 1));
+          r_acc += rew_a;
+          d_cnt += nd_a ? 0u : 1u;
+        }
+        if (live_b) {
+          __stcs(so + kB, nb);
+          __stcs(ro + kB, rew_b);
+          __stcs(dn + kB, static_cast<uint8_t>(nd_b ? 0 : 1));
+          r_acc += rew_b;
+          d_cnt += nd_b ? 0u : 1u;
+        }
+        if (false)
+#endif
         if (live_a) {
           so[0] = na;
           if constexpr (HAS_OBS) obs_out[i] = oa;
