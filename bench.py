@@ -375,7 +375,8 @@ class CartPoleStep(Workload):
         self.env0 = self.envs[0]
         self.env0.step_host(self.act_host[0])
         self.h2d, self.d2h = self.env0._staging.h2d_bytes, self.env0._staging.d2h_bytes
-        self.e2e_api = "env.step_host(action_host) -> numpy obs/reward/terminated (pinned staging, chunked copy/compute overlap)"
+        self.e2e_api = ("env.step_host(action_host) -> numpy obs/reward/terminated (pinned staging; >= 2^17 envs: chunked copy/compute overlap through the "
+                        "copy engines; <= 2^16 envs: the kernel loads / stores the pinned host arrays itself)")
 
     e2e_warmup = 24  # 4 pinned action buffers x 2 ping-pong sides, each seen eagerly, captured, replayed
 

@@ -10,6 +10,7 @@ HBM layout:
 """
 import ctypes
 import gc
+import os
 from typing import Optional
 
 import numpy as np
@@ -391,6 +392,10 @@ class I2PEngine(RolloutMixin):
 class ChargedBallEngine(RolloutMixin):
     """charged ball (emei_charged_ball_step_*): three state arrays updated in place."""
 
+    # step_host: the observation is the `free` state array itself, so it needs a copy anyway and kernel-side stores of
+    # reward / done alone measured slower than the DMA path (16384 envs: 50.8 us against 41.5)
+    zero_copy_ok = False
+
     def rollout(self, rp: _lib.RolloutParams, actions, record: bool, rollout_stats: torch.Tensor, noise=None):
         ptrs = [self.on_circle.data_ptr(), self.circle.data_ptr(), self.free.data_ptr()]
         if self.env.dtype == torch.float32:
@@ -631,6 +636,10 @@ def time_fused_scoring(env, obs, pre_obs, action, reps=10):
     return e0.elapsed_time(e1) / reps
 
 
+ZERO_COPY_MAX_ENVS = 65536  # measured: scripts/probe_zero_copy_small.py, profiles/r02_zero_copy_small.txt
+ZERO_COPY_ACTION_MAX_ENVS = 8192  # = the small-batch kernel's limit (cartpole_tma.cuh): plain loads below it
+
+
 class HostStaging:
     """Pinned host buffers + the copy choreography of ``step_host`` (the end-to-end path with HOST
     inputs and outputs).  The env batch is cut into ``chunks`` contiguous ranges, each on its own
@@ -681,6 +690,9 @@ class HostStaging:
         self.streams = [torch.cuda.Stream(dev) for _ in self.ranges]
         self.done_host_u8 = self.done_host.view(torch.uint8)
         self.use_graphs = True
+        # kernel-side loads / stores of the pinned host arrays instead of DMA transfers (see _enqueue); EMEI_ZERO_COPY_MAX
+        # overrides the batch-size limit (0 disables)
+        self.zero_copy = n <= int(os.environ.get("EMEI_ZERO_COPY_MAX", ZERO_COPY_MAX_ENVS)) and getattr(env._engine, "zero_copy_ok", True)
         self._capture_stream = torch.cuda.Stream(dev)
         self._graphs, self._seen, self._keep, self._pinned = {}, {}, {}, {}
 
@@ -692,7 +704,22 @@ class HostStaging:
         cur = torch.cuda.current_stream(env.device)
         kw = {} if noise is None else {"noise": noise}
         want = self.outputs
-        if len(self.ranges) == 1:  # small batch: latency-bound, no side streams
+        if len(self.ranges) == 1 and self.zero_copy:
+            # Small batch: the host step is pure latency (a 4096-env step is three copy-engine transfers of a few KB
+            # around a 2 us kernel, ~10 us each).  A page-locked host buffer IS device-addressable (UVA), so the kernel
+            # reads the actions from the caller's pinned array and stores reward / done / obs straight into the pinned
+            # result arrays: one launch, no DMA transfers.  Same bytes over PCIe, moved by the SMs' loads and stores.
+            # (At 2^20 envs the copy engines win -- 0.49 ms against 0.55 -- so this is for small batches only.)
+            act = a_src
+            if env.num_envs >= ZERO_COPY_ACTION_MAX_ENVS:  # the large-batch step kernel stages its actions with bulk (TMA) copies:
+                self.a_dev.copy_(a_src, non_blocking=True)  # those read device memory, so the actions take the DMA path there
+                act = self.a_dev
+            obs = eng.step_range(0, env.num_envs, act, self.rew_host if "reward" in want else self.rew_dev,
+                                 self.done_host_u8 if "done" in want else self.done_dev, self.obs_host if "obs" in want else None, **kw)
+            if "obs" in want and obs is not self.obs_host:  # families whose observation is the state array itself
+                self.obs_host.copy_(obs, non_blocking=True)
+            return
+        if len(self.ranges) == 1:  # one range, copy engines: no side streams
             self.a_dev.copy_(a_src, non_blocking=True)
             obs = eng.step_range(0, env.num_envs, self.a_dev, self.rew_dev, self.done_dev, None, **kw)
             if "obs" in want:
