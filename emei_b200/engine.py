@@ -695,6 +695,7 @@ class HostStaging:
         self.zero_copy = n <= int(os.environ.get("EMEI_ZERO_COPY_MAX", ZERO_COPY_MAX_ENVS)) and getattr(env._engine, "zero_copy_ok", True)
         self._capture_stream = torch.cuda.Stream(dev)
         self._graphs, self._seen, self._keep, self._pinned = {}, {}, {}, {}
+        self._np_views = None
 
     # ---- one host step ---------------------------------------------------------------------------
     def _enqueue(self, a_src, noise=None):
@@ -747,8 +748,10 @@ class HostStaging:
 
     def _result(self):
         w = self.outputs
-        return (self.obs_host.numpy() if "obs" in w else None, self.rew_host.numpy() if "reward" in w else None,
-                self.done_host.numpy() if "done" in w else None, False, {})
+        v = self._np_views  # the numpy views of the pinned result arrays are made once (a small host step is latency)
+        if v is None:
+            v = self._np_views = {"obs": self.obs_host.numpy(), "reward": self.rew_host.numpy(), "done": self.done_host.numpy()}
+        return (v["obs"] if "obs" in w else None, v["reward"] if "reward" in w else None, v["done"] if "done" in w else None, False, {})
 
     def step(self, action, outputs=None):
         """``outputs``: subset of ("obs", "reward", "done") to download (default: all three, the reference's step()
@@ -766,12 +769,14 @@ class HostStaging:
         outs = self.ALL_OUTPUTS if outputs is None else tuple(o for o in self.ALL_OUTPUTS if o in outputs)
         if outputs is not None and (len(outs) != len(tuple(outputs)) or not outs):
             raise ValueError(f"outputs must be a non-empty subset of {self.ALL_OUTPUTS}, got {outputs!r}")
-        self.outputs = outs
-        self.d2h_bytes = sum(self._out_bytes[o] for o in outs)
+        if outs != self.outputs or self.d2h_bytes == 0:
+            self.outputs = outs
+            self.d2h_bytes = sum(self._out_bytes[o] for o in outs)
         a = torch.as_tensor(action)
         if a.is_cuda:
             raise TypeError("step_host takes host actions; use step() for device tensors")
-        a = a.reshape(-1)
+        if a.dim() != 1:
+            a = a.reshape(-1)
         if a.numel() != self.a_host.numel():
             raise ValueError(f"step_host: expected {self.a_host.numel()} actions, got {a.numel()}")
         ptr = a.data_ptr()
