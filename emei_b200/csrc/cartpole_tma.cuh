@@ -15,6 +15,7 @@
 //
 // Chunk c = envs [512 c, 512 c + 512): thread t of a group owns envs 512 c + t and 512 c + 256 + t.
 #pragma once
+#include <cstdlib>
 #include <type_traits>
 #include "cartpole_f32.cuh"
 
@@ -535,7 +536,8 @@ inline cudaError_t launch_pdl_smem(void (*kernel)(KArgs...), int grid, int block
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  static const bool no_pdl = getenv("EMEI_NO_PDL") != nullptr;  // development A/B: ordinary stream order (griddepcontrol.* become no-ops)
+  cfg.numAttrs = no_pdl ? 0 : 1;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
