@@ -782,7 +782,28 @@ class ScoringSweepSeq(ScoringSweep):
         self.cp.unfreeze()
 
     def setup_e2e(self):
-        return Workload.setup_e2e(self)
+        import torch
+
+        m_traj = self.e2e_half // self.T  # trajectories per family of the host-buffer sample
+        self.h_in = [[seq[:, :m_traj].contiguous().cpu().pin_memory(), act[:, :m_traj].contiguous().cpu().pin_memory()] for seq, act in self.data]
+        m = m_traj * self.T
+        self.h_out = [(torch.empty((m, 1), dtype=torch.float32).pin_memory(), torch.empty((m, 1), dtype=torch.bool).pin_memory()) for _ in range(2)]
+        self.h2d = sum(t.numel() * t.element_size() for fam in self.h_in for t in fam)
+        self.d2h = 2 * m * 5
+        self.e2e_units = 2 * m
+        self.e2e_api = (f"freeze(); hopper / halfcheetah get_batch_reward_terminal_seq on pinned HOST trajectory tensors ({m_traj} trajectories x {self.T} steps "
+                        "each: a bounded sample of the sweep, the rate is per transition) -> results copied back to pinned host; unfreeze()")
+
+    def step_e2e(self, i):
+        import torch
+
+        self.cp.freeze()
+        for env, h_in, (h_r, h_d) in zip((self.hop, self.chee), self.h_in, self.h_out):
+            r, d = env.get_batch_reward_terminal_seq(*h_in)
+            h_r.copy_(r.reshape(-1, 1), non_blocking=True)
+            h_d.copy_(d.reshape(-1, 1), non_blocking=True)
+        self.cp.unfreeze()
+        torch.cuda.current_stream(self.dev).synchronize()
 
     @classmethod
     def config(cls, args, world):
@@ -888,7 +909,7 @@ class CartPoleRolloutRecord(CartPoleRollout):
     title = CartPoleRollout.title.replace("fused rollout", "fused rollout + transition records (dataset layout)")
     kernel = "emei::rollout_f32_kernel<CartPoleDyn<IP=0, AK=f32, FR=4>, RECORD=1>"
     record = True
-    inst_per_unit = 289.9  # ncu, profiles/r01_launches_rollout_rec.csv
+    inst_per_unit = 223.8  # ncu, profiles/r02_launches_rollout_rec.csv (289.9 before the spare reset samples)
 
 
 class ChargedBallRollout(Workload):
