@@ -906,7 +906,9 @@ def test_empty_and_ragged_batches():
 # ================================================================================================
 # step_host: the end-to-end host path (chunked multi-stream pipeline) must equal step() bit for bit
 # ================================================================================================
-@pytest.mark.parametrize("n", (1000, 300_000, 1_100_003))  # one range, one range, two unequal ranges with a ragged end
+# 1000: the kernel reads / writes the pinned host arrays itself (small-batch kernel); 20 000: the same through the TMA kernel (actions by
+# DMA, results stored to host memory); 300 000: one range through the copy engines; 1 100 003: two unequal ranges with a ragged end
+@pytest.mark.parametrize("n", (1000, 20_000, 300_000, 1_100_003))
 @pytest.mark.parametrize("env_id", ("ContinuousCartPoleSwingUp-v0", "CartPoleBalancing-v0", "BoundaryInvertedPendulumSwingUp-v0",
                                     "ChargedBallCentering-v0", "BoundaryInvertedDoublePendulumSwingUp-v0"))
 def test_step_host_equals_step(env_id, n):
