@@ -1821,3 +1821,20 @@ def test_step_host_outputs_selector(env_id, n):
     assert _same_state(a.state, b.state)
     with pytest.raises(ValueError):
         b.step_host(act, outputs=("observation",))
+
+
+def test_random_policy_test_mirror():
+    """emei/util.py:5-41 batched (emei_b200.util.random_policy_test): the reference's report line, the random and the
+    constant-action policy, a bounded run."""
+    from emei_b200.util import random_policy_test
+
+    env = E.make("CartPoleBalancing-v0", num_envs=256, dtype=torch.float32)
+    lines = []
+    rep = random_policy_test(env, report_every=50, max_steps=100, out=lines.append)
+    assert len(rep) == 2 and sum(r["total_episode_num"] for r in rep) > 0
+    assert lines and lines[0].startswith("episode length: ") and "\tepisode rewards: " in lines[0]
+    rep = random_policy_test(env, default_action=1, report_every=40, max_steps=40, out=lines.append)
+    assert rep[0]["total_episode_num"] >= env.num_envs  # pushing right at every step ends every episode within 40 steps
+    assert rep[0]["terminated"] >= env.num_envs and rep[0]["avg_length"] < 40
+    with pytest.raises(NotImplementedError):
+        random_policy_test(env, is_render=True)
