@@ -246,6 +246,29 @@ __device__ __forceinline__ float py_mod(float a, float b) {
   return m;
 }
 
+// python `a % 2` (the double pendulum's observation, inverted_double_pendulum.py:59) without fmod's remainder loop:
+// a - 2 trunc(a / 2) consists of exact operations only for every finite a (a / 2 and 2 t are scalings by a power of two; for
+// |a| >= 2^p the float is an even integer and the difference is 0, below that the difference of the two is representable), so it
+// IS fmod(a, 2) -- same bits, the sign of a zero aside, which python's fix-up below discards; Inf -> NaN, NaN -> NaN like fmod.
+__device__ __forceinline__ double py_mod2(double a) {
+  double m = a - 2.0 * trunc(a * 0.5);
+  if (m != 0.0) {
+    if (m < 0.0) m += 2.0;
+  } else {
+    m = 0.0;
+  }
+  return m;
+}
+__device__ __forceinline__ float py_mod2(float a) {
+  float m = a - 2.0f * truncf(a * 0.5f);
+  if (m != 0.0f) {
+    if (m < 0.0f) m += 2.0f;
+  } else {
+    m = 0.0f;
+  }
+  return m;
+}
+
 // float32 observation wrap `(theta + pi) % (2 pi) - pi` (inverted_pendulum.py:45-49) by Cody-Waite
 // reduction: exact for |theta| < pi (forming theta + pi in float32 would cost 1.2e-7 of the 1e-6 budget),
 // error <= ulp(theta) beyond.  Result in [-pi_f, pi_f); NaN / Inf -> NaN like the reference.

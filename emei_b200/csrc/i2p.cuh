@@ -157,15 +157,15 @@ __device__ __forceinline__ void i2p_env_step(R (&y)[6], R ctrl, const I2PConsts<
   }
   // inverted_double_pendulum.py:56-60: (theta + pi) % 2 * pi - pi   (sic)
   o[0] = y[0];
-  o[1] = py_mod(y[1] + k.pi, R(2)) * k.pi - k.pi;
-  o[2] = py_mod(y[2] + k.pi, R(2)) * k.pi - k.pi;
+  o[1] = py_mod2(y[1] + k.pi) * k.pi - k.pi;
+  o[2] = py_mod2(y[2] + k.pi) * k.pi - k.pi;
   o[3] = y[3], o[4] = y[4], o[5] = y[5];
   // get_batch_reward / get_batch_terminal of the variant on that observation, fused (the expressions of
   // reward_terminal_kernel's I2P families: inverted_double_pendulum.py:84-90,114-122,150-157,185-196)
   bool finite = true;
 #pragma unroll
   for (int j = 0; j < 6; ++j) finite = finite && is_finite(o[j]);
-  const R yy = cos_r(o[1]) + cos_r(o[1] + o[2]);
+  const R yy = cos_obs(o[1]) + cos_obs(o[1] + o[2]);
   const bool in_rail = (k.x_left < o[0]) && (o[0] < k.x_right);
   switch (k.variant) {
     case EMEI_I2P_REBOUND_BALANCING:

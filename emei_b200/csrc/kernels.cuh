@@ -6,6 +6,7 @@
 // expressions below follow the reference's python line by line (file:line cited at each block).
 #pragma once
 #include "common.cuh"
+#include "f32math.cuh"
 
 namespace emei {
 
@@ -110,6 +111,17 @@ __device__ __forceinline__ void add_state_noise(R (&y)[DIM], const NoiseConsts& 
 // One env step on registers: the whole of BaseControlEnv.step for one env (shared by the step kernel and the
 // reference-arithmetic rollout kernel of rollout_ref.cuh: same bits).  drive = the force (cart-pole family,
 // cartpole.py:121-122,142-143) or the raw control value (IP: clamped to ctrlrange like mj_step, then x gear).
+// cos of an observation angle in the double pendulum's scores (the fused step of i2p.cuh and the I2P scoring families share it,
+// so get_batch_reward(obs) equals the step's own reward bit for bit): float32 = the lean kernel of f32math.cuh (|error| <= 7e-8 up to
+// |x| = 1e5, libm beyond and for NaN / Inf), float64 = libm like the oracle.
+template <typename R>
+__device__ __forceinline__ R cos_obs(R x) {
+  if constexpr (sizeof(R) == 4)
+    return f32::cos_fast(x);
+  else
+    return cos(x);
+}
+
 template <typename R, bool IP>
 __device__ __forceinline__ void cartpole_env_step(Vec4<R>& y, R drive, const CartPoleConsts<R>& k, const NoiseConsts& z,
                                                   unsigned long long env, unsigned long long substep0, R& rew, bool& notdone,
@@ -522,7 +534,7 @@ __device__ __forceinline__ void score_row(const R (&o)[D], R p0, R ctrl_cost, co
     }
   } else if constexpr (FAMILY >= EMEI_I2P_REBOUND_BALANCING && FAMILY <= EMEI_I2P_BOUNDARY_SWINGUP) {
     const bool finite = row_finite<R, D>(o);
-    const R y = cos_r(o[1]) + cos_r(o[1] + o[2]);  // inverted_double_pendulum.py:88
+    const R y = cos_obs(o[1]) + cos_obs(o[1] + o[2]);  // inverted_double_pendulum.py:88 (the fused step's expression: same bits)
     const bool in_rail = (k.x_left < o[0]) && (o[0] < k.x_right);
     if constexpr (FAMILY == EMEI_I2P_REBOUND_BALANCING) {  // :84-90
       rew = R(1);

@@ -148,8 +148,8 @@ struct RefI2P {
   __device__ __forceinline__ static void store(const Regs& e, const Buffers& b, int64_t i) { i2p_store_row<R>(b.state, i, true, e.y); }
   __device__ __forceinline__ static void observation(const Regs& e, const Consts& k, R (&o)[kObs]) {
     o[0] = e.y[0];
-    o[1] = py_mod(e.y[1] + k.pi, R(2)) * k.pi - k.pi;  // inverted_double_pendulum.py:56-60 (sic)
-    o[2] = py_mod(e.y[2] + k.pi, R(2)) * k.pi - k.pi;
+    o[1] = py_mod2(e.y[1] + k.pi) * k.pi - k.pi;  // inverted_double_pendulum.py:56-60 (sic)
+    o[2] = py_mod2(e.y[2] + k.pi) * k.pi - k.pi;
     o[3] = e.y[3], o[4] = e.y[4], o[5] = e.y[5];
   }
   __device__ __forceinline__ static R drive(const Consts&, const void* actions, const RefAction& a, int kind) {
