@@ -863,7 +863,7 @@ class CartPoleRollout(Workload):
         self.act_host = [torch.as_tensor(rng.uniform(-1, 1, size=(self.T, self.n_envs)).astype(np.float32)).pin_memory() for _ in range(2)]
         self.h2d = self.act_host[0].numel() * 4
         self.d2h = 48
-        self.e2e_api = "env.rollout(horizon, actions=pinned HOST [T,n] float32) -> env.rollout_info(stats) read on the host"
+        self.e2e_api = "env.rollout(horizon, actions=pinned HOST [T,n] float32) -> env.rollout_info(stats) read on the host (the horizon is cut into pieces whose uploads run one piece ahead of the kernels)"
 
     def step_e2e(self, i):
         out = self.env.rollout(self.T, actions=self.act_host[i % 2])
@@ -964,7 +964,7 @@ class ChargedBallRollout(Workload):
         self.act_host = [torch.randint(0, 2, (self.Te, self.n), dtype=torch.uint8, generator=g).pin_memory() for _ in range(2)]
         self.h2d, self.d2h = self.Te * self.n, 48
         self.e2e_units = self.n * self.Te
-        self.e2e_api = f"env.rollout({self.Te}, actions=pinned HOST uint8[{self.Te}, n]) -> env.rollout_info(stats) read on the host"
+        self.e2e_api = f"env.rollout({self.Te}, actions=pinned HOST uint8[{self.Te}, n]) -> env.rollout_info(stats) read on the host (the horizon is cut into pieces whose uploads run one piece ahead of the kernels)"
 
     def step_e2e(self, i):
         out = self.env.rollout(self.Te, actions=self.act_host[i % 2])

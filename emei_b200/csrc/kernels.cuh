@@ -206,6 +206,8 @@ __global__ void __launch_bounds__(kBlock)
   const int64_t stride = static_cast<int64_t>(gridDim.x) * kBlock;
   double r_acc = 0.0;
   unsigned d_cnt = 0;
+  pdl_trigger();  // programmatic dependent launch (common.cuh): the next step's CTAs are staged while this grid's tail drains
+  pdl_wait();
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * kBlock + threadIdx.x; i < n; i += stride) {
     Vec4<R> y = Vec4<R>::load(state_in + 4 * i), obs;
     const R drive = IP ? load_ctrl<R>(action, i, k.action_kind) : load_force<R>(action, i, k.action_kind, k.force_mag);
@@ -258,11 +260,11 @@ int cartpole_step(const R* state_in, R* state_out, R* obs_out, const void* actio
   const CartPoleConsts<R> k = make_cartpole_consts<R>(*p);
   const NoiseConsts z = make_noise_consts(noise, p->freq_rate);
   if (p->variant <= EMEI_CARTPOLE_SWINGUP)
-    cartpole_step_kernel<R, false><<<resident_grid(cartpole_step_kernel<R, false>, n), kBlock, 0, s>>>(
-        state_in, state_out, obs_out, action, reward, done, stats, n, k, z);
+    launch_pdl(cartpole_step_kernel<R, false>, resident_grid(cartpole_step_kernel<R, false>, n), kBlock, s, state_in, state_out, obs_out,
+               action, reward, done, stats, n, k, z);
   else
-    cartpole_step_kernel<R, true><<<resident_grid(cartpole_step_kernel<R, true>, n), kBlock, 0, s>>>(
-        state_in, state_out, obs_out, action, reward, done, stats, n, k, z);
+    launch_pdl(cartpole_step_kernel<R, true>, resident_grid(cartpole_step_kernel<R, true>, n), kBlock, s, state_in, state_out, obs_out,
+               action, reward, done, stats, n, k, z);
   return launch_status();
 }
 

@@ -1838,3 +1838,29 @@ def test_random_policy_test_mirror():
     assert rep[0]["terminated"] >= env.num_envs and rep[0]["avg_length"] < 40
     with pytest.raises(NotImplementedError):
         random_policy_test(env, is_render=True)
+
+
+@pytest.mark.parametrize("env_id,cont", (("ChargedBallCentering-v0", False), ("ContinuousCartPoleSwingUp-v0", True)))
+def test_rollout_with_host_actions_is_pipelined_and_equal(env_id, cont, monkeypatch):
+    """Teacher-forced rollouts whose actions are HOST arrays are cut into pieces (uploads one piece ahead of the kernels):
+    same final state, counters and statistics as one launch over the same actions on the device."""
+    n, T = 3000, 40
+    rng = np.random.default_rng(9)
+    acts = rng.uniform(-1, 1, size=(T, n)).astype(np.float32) if cont else rng.integers(0, 2, size=(T, n)).astype(np.uint8)
+    a = E.make(env_id, num_envs=n, dtype=torch.float32)
+    b = E.make(env_id, num_envs=n, dtype=torch.float32)
+    a.reset(seed=4)
+    b.reset(seed=4)
+    monkeypatch.setattr(type(b), "_ROLLOUT_PIECE_BYTES", 3 * acts[0].nbytes)  # pieces of 3 steps: 14 launches, a ragged last one
+    monkeypatch.setattr(type(b), "_ROLLOUT_PIECE_MIN_STEPS", 1)
+    launches0 = E._lib.launch_count
+    out_b = b.rollout(T, actions=torch.as_tensor(acts).pin_memory(), max_episode_steps=7)
+    assert E._lib.launch_count - launches0 == 14
+    out_a = a.rollout(T, actions=torch.as_tensor(acts).cuda(), max_episode_steps=7)
+    assert _same_state(a.state, b.state)
+    assert torch.allclose(out_a["stats"], out_b["stats"], rtol=1e-12, atol=0)
+    for k in ("ep_step", "ep_index", "ep_return"):
+        assert torch.equal(getattr(a._engine, k), getattr(b._engine, k)), k
+    out_c = b.rollout(T, actions=acts, max_episode_steps=7)  # pageable numpy actions take the same path
+    out_d = a.rollout(T, actions=torch.as_tensor(acts).cuda(), max_episode_steps=7)
+    assert _same_state(a.state, b.state) and torch.allclose(out_c["stats"], out_d["stats"], rtol=1e-12, atol=0)
