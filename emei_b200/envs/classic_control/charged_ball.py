@@ -7,10 +7,7 @@ is implemented is the semantics of the physics helpers (:25-82), batched, with t
 observation is ``free`` (:96-97).  Constructor keywords follow the reference: ``freq_rate``,
 ``time_step`` (the reference then overwrites time_step with 0.02, :17 -- replicated).
 """
-import torch
-
 from ... import _lib, spaces
-from ...core import EmeiEnv
 from ...engine import ChargedBallEngine, normalise_action, score
 from .base_control import BaseControlEnv
 

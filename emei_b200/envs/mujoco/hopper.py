@@ -12,8 +12,6 @@ Replicated reference behaviour:
 """
 from typing import Tuple
 
-import torch
-
 from ... import _lib
 from ...engine import score
 from .mujoco_env import EmeiMujocoEnv
