@@ -15,7 +15,6 @@ Two derivations, both evaluated with sympy on the same random states:
   engine implements ``acc_physical``; the oracle restates both and is pinned against both.
 """
 import os
-import pickle
 import sys
 import types
 
