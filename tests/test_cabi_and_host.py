@@ -389,3 +389,22 @@ def test_round2_entry_points_validate_arguments_without_a_gpu():
         cb = _lib.ChargedBallParams()
         cr = getattr(L, "emei_charged_ball_rollout_ref" + sfx)
         assert cr(*([None] * 14), 4, ctypes.byref(cb), ctypes.byref(rp), None) == -6         # EMEI_ERR_BAD_PARAM (freq_rate 0)
+
+
+def test_plan_rollout_pieces():
+    """core.EmeiEnv.plan_rollout_pieces: how a teacher-forced rollout with HOST actions is cut for upload / kernel overlap."""
+    from emei_b200.core import EmeiEnv
+
+    plan = EmeiEnv.plan_rollout_pieces
+    mb = 1 << 20
+    # C4's end-to-end leg: 25 steps of 2^26 uint8 actions (64 MB per step): 8-step pieces, a ragged last one
+    assert plan(25, 64 * mb, 32 * mb, 8) == [(0, 8), (8, 16), (16, 24), (24, 25)]
+    # cart-pole: 100 steps of 2^20 float32 actions (4 MB per step): 32 MB = 8 steps per piece
+    p = plan(100, 4 * mb, 32 * mb, 8)
+    assert p[0] == (0, 8) and p[-1] == (96, 100) and len(p) == 13
+    assert all(a[1] == b[0] for a, b in zip(p, p[1:]))  # a tiling
+    # small rollouts stay one upload + one launch
+    assert plan(15, 64 * mb, 32 * mb, 8) is None        # fewer than two pieces
+    assert plan(100, 4096, 32 * mb, 8) is None          # 400 KB in total
+    assert plan(40, 3000, 9000, 1) == [(lo, min(40, lo + 3)) for lo in range(0, 40, 3)]  # the GPU test's shape
+    assert plan(0, 4 * mb, 32 * mb, 8) is None
