@@ -445,7 +445,7 @@ class I2PStep(CartPoleStep):
     alg_bytes_f64 = 157
     alg_fp_ops = alg_sfu_ops = None  # SURVEY 8d states no operation count for the 3x3 Lagrangian solve
     cpu_kind, cpu_sample = "i2p", 1 << 18
-    inst_per_unit = 342.7  # 32 x smsp__inst_executed / envs (ncu, profiles/r01_launches_i2p.csv)
+    inst_per_unit = 334.6  # 32 x smsp__inst_executed / envs (ncu, profiles/r02_ncu_full_i2p.txt: 10 963 240 warp instructions per 2^20-env launch)
 
     def synth(self, seed):
         return synth_i2p(self.n_envs, seed)
